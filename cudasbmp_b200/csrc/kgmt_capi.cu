@@ -1,0 +1,860 @@
+/* kgmt_capi.cu — the C ABI of libkgmt_b200.so (include/kgmt_c.h) over the sm_100a
+ * kernels in kgmt_kernels.cuh.  Host side of the KGMT tree-expansion path:
+ * context = what the reference's KGMT constructor allocates
+ * (src/planners/KGMT.cu:10-78), kgmt_plan = KGMT::plan (:80-317).
+ *
+ * No CPU fallback: every entry point that computes launches CUDA kernels; a
+ * missing device is KGMT_ERR_CUDA.  Nothing here touches oracle/.
+ */
+#include "kgmt_c.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kgmt_kernels.cuh"
+
+using namespace kgmt;
+
+struct kgmt_ctx {
+    kgmt_params p;
+    int device = 0, numSMs = 0, maxCand = 0, c1 = 0;
+    size_t c2 = 0;
+    float R1Size = 0.f, R2Size = 0.f;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    /* device memory */
+    float4 *treeState = nullptr, *treeCtrl = nullptr;
+    int* treeParent = nullptr;
+    int* mapSlab = nullptr;            /* [R1,R1Valid,R1Invalid,R1Avail,R1Cov,R1Score | R2,R2Valid,R2Invalid,R2Stamp] */
+    int* mapSlabCkpt = nullptr;
+    size_t mapSlabInts = 0;
+    int *R1 = nullptr, *R1Valid = nullptr, *R1Invalid = nullptr, *R1Avail = nullptr, *R1Cov = nullptr;
+    float* R1Score = nullptr;
+    int *R2 = nullptr, *R2Valid = nullptr, *R2Invalid = nullptr;
+    unsigned* R2Stamp = nullptr;
+    float4 *candState = nullptr, *candCtrl = nullptr;
+    int *candParent = nullptr, *candR1 = nullptr, *candR2 = nullptr;
+    unsigned char* candFlags = nullptr;
+    bool recordAllocated = false;
+    unsigned long long* tileStatus = nullptr;
+    DevState* dState = nullptr;
+    DevState* hState = nullptr;        /* pinned */
+    DevState ckptState{};
+    bool haveCkpt = false;
+    /* obstacles and the cull grid */
+    float4* dObs = nullptr; int K = 0; size_t obsCap = 0;
+    int* dCellStart = nullptr; float4* dCellItems = nullptr; size_t cellStartCap = 0, cellItemsCap = 0;
+    int cullC = 1, cellStartInts = 4, numItems = 0;
+    float cullInvX = 0.f, cullInvY = 0.f;
+    std::vector<float> hObs;
+    /* staging */
+    void* scratch = nullptr; size_t scratchBytes = 0;
+    float4* dParents = nullptr; size_t parentsCap = 0;
+    /* launch configuration */
+    int col = COL_GRID_SMEM; size_t smemBytes = 0; int useHist = 0;
+    int gridLoop = 0, gridMax = 0;
+    bool configured = false;
+    bool begun = false;
+    float goal[7] = {0};
+    long long launches = 0;
+    int planLaunches = 0;
+    size_t dirtyTree = 0, dirtyCand = 0;   /* rows a plan may have written since the last clear */
+    unsigned epochBase = 0;
+    DevState resetState{};
+    char err[512] = {0};
+};
+
+/* -------------------------------------------------------------------------------- errors */
+static int fail(kgmt_ctx* c, int code, const char* fmt, ...) {
+    if (c) {
+        va_list ap; va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(ctx, KGMT_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+static const size_t MAX_DYN_SMEM = 227u * 1024u - 8u * 1024u;   /* leave room for static shared + reserve */
+
+/* -------------------------------------------------------------------------------- kernels table */
+typedef void (*expand_fn)(const KArgs);
+template <int COL> static expand_fn pick_expand(bool loop, bool rec) {
+    if (loop) return rec ? (expand_fn)expand_kernel<COL, true, true> : (expand_fn)expand_kernel<COL, true, false>;
+    return rec ? (expand_fn)expand_kernel<COL, false, true> : (expand_fn)expand_kernel<COL, false, false>;
+}
+static expand_fn expand_entry(int col, bool loop, bool rec) {
+    switch (col) {
+        case COL_GRID_SMEM: return pick_expand<COL_GRID_SMEM>(loop, rec);
+        case COL_GRID_GLOBAL: return pick_expand<COL_GRID_GLOBAL>(loop, rec);
+        case COL_BRUTE_SMEM: return pick_expand<COL_BRUTE_SMEM>(loop, rec);
+        default: return pick_expand<COL_BRUTE_GLOBAL>(loop, rec);
+    }
+}
+typedef void (*prop_fn)(const KArgs, const float4*, long long, int, uint32_t, uint32_t);
+static prop_fn propagate_entry(int col) {
+    switch (col) {
+        case COL_GRID_SMEM: return propagate_only_kernel<COL_GRID_SMEM>;
+        case COL_GRID_GLOBAL: return propagate_only_kernel<COL_GRID_GLOBAL>;
+        case COL_BRUTE_SMEM: return propagate_only_kernel<COL_BRUTE_SMEM>;
+        default: return propagate_only_kernel<COL_BRUTE_GLOBAL>;
+    }
+}
+
+static KArgs make_args(const kgmt_ctx* c) {
+    KArgs A{};
+    A.treeState = c->treeState; A.treeCtrl = c->treeCtrl; A.treeParent = c->treeParent;
+    A.R1 = c->R1; A.R1Valid = c->R1Valid; A.R1Invalid = c->R1Invalid; A.R1Avail = c->R1Avail; A.R1Cov = c->R1Cov;
+    A.R1Score = c->R1Score;
+    A.R2 = c->R2; A.R2Valid = c->R2Valid; A.R2Invalid = c->R2Invalid; A.R2Stamp = c->R2Stamp;
+    A.candState = c->candState; A.candCtrl = c->candCtrl; A.candParent = c->candParent;
+    A.candR1 = c->candR1; A.candR2 = c->candR2; A.candFlags = c->candFlags;
+    A.tileStatus = c->tileStatus; A.st = c->dState;
+    A.obstacles = c->dObs; A.K = c->K;
+    A.cellStart = c->dCellStart; A.cellItems = c->dCellItems; A.cullC = c->cullC;
+    A.cullInvX = c->cullInvX; A.cullInvY = c->cullInvY; A.cellStartInts = c->cellStartInts; A.numItems = c->numItems;
+    A.obsTile = 0;
+    A.W = c->p.width; A.H = c->p.height; A.L = c->p.agent_length; A.R1Size = c->R1Size; A.R2Size = c->R2Size;
+    A.goalX = c->goal[0]; A.goalY = c->goal[1]; A.goalR = c->p.goal_threshold;
+    A.N = c->p.N; A.n = c->p.n; A.c1 = c->c1; A.numDisc = c->p.num_disc; A.maxTree = c->p.max_tree_size;
+    A.numIterations = c->p.num_iterations; A.useHist = c->useHist;
+    A.seed = c->p.seed;
+    return A;
+}
+
+/* choose the collision back end + shared memory, set kernel attributes, size the persistent grid */
+static int configure(kgmt_ctx* ctx) {
+    const size_t histBytes = ctx->useHist ? (((size_t)2 * ctx->c1 * 4 + 15) & ~(size_t)15) : 0;
+    const size_t limit = ctx->p.reserved[0] > 0 ? (size_t)ctx->p.reserved[0] : (size_t)48 * 1024;   /* staging budget */
+    size_t colBytes = 0;
+    int col;
+    if (ctx->p.collision_mode == KGMT_COLLIDE_BRUTE) {
+        colBytes = (size_t)ctx->K * 16;
+        col = (histBytes + colBytes <= MAX_DYN_SMEM) ? COL_BRUTE_SMEM : COL_BRUTE_GLOBAL;
+    } else {
+        colBytes = (size_t)ctx->cellStartInts * 4 + (size_t)ctx->numItems * 16;
+        col = (colBytes <= limit && histBytes + colBytes <= MAX_DYN_SMEM) ? COL_GRID_SMEM : COL_GRID_GLOBAL;
+    }
+    if (col == COL_GRID_GLOBAL || col == COL_BRUTE_GLOBAL) colBytes = 0;
+    ctx->col = col;
+    ctx->smemBytes = histBytes + colBytes;
+    int occ = 0;
+    for (int loop = 0; loop < 2; ++loop)
+        for (int rec = 0; rec < 2; ++rec) {
+            expand_fn f = expand_entry(col, loop, rec);
+            CU(cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemBytes));
+            int o = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void*)f, TILE, ctx->smemBytes));
+            if (loop == 1 && rec == (ctx->p.record_candidates ? 1 : 0)) occ = o;
+        }
+    CU(cudaFuncSetAttribute((const void*)propagate_entry(col), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)colBytes));
+    if (occ < 1) return fail(ctx, KGMT_ERR_CUDA, "expand kernel does not fit on an SM (smem %zu B)", ctx->smemBytes);
+    ctx->gridLoop = occ * ctx->numSMs;
+    ctx->gridMax = occ * ctx->numSMs;
+    ctx->configured = true;
+    return KGMT_OK;
+}
+
+/* uniform grid over the workspace: CSR of obstacle AABBs per cell (host build) */
+static int cull_cell(float v, float inv, int C) {
+    const float t = std::floor(v * inv);
+    if (!(t > 0.0f)) return 0;
+    if (t >= (float)C) return C - 1;
+    return (int)t;
+}
+static int build_cull_grid(kgmt_ctx* ctx) {
+    const int K = ctx->K;
+    int C = ctx->p.cull_cells;
+    if (C <= 0) C = (int)std::ceil(std::sqrt((double)std::max(K, 1)));
+    C = std::max(1, std::min(C, 512));
+    const float invX = (float)C / ctx->p.width, invY = (float)C / ctx->p.height;
+    std::vector<int> start((size_t)C * C + 1, 0);
+    const float* o = ctx->hObs.data();
+    for (int k = 0; k < K; ++k) {
+        const int x0 = cull_cell(o[4 * k], invX, C), x1 = cull_cell(o[4 * k + 2], invX, C);
+        const int y0 = cull_cell(o[4 * k + 1], invY, C), y1 = cull_cell(o[4 * k + 3], invY, C);
+        for (int y = y0; y <= y1; ++y)
+            for (int x = x0; x <= x1; ++x) start[(size_t)y * C + x + 1] += 1;
+    }
+    for (size_t i = 0; i < (size_t)C * C; ++i) start[i + 1] += start[i];
+    const int numItems = start[(size_t)C * C];
+    std::vector<float> items((size_t)std::max(numItems, 1) * 4, 0.0f);
+    std::vector<int> fill(start.begin(), start.end() - 1);
+    for (int k = 0; k < K; ++k) {
+        const int x0 = cull_cell(o[4 * k], invX, C), x1 = cull_cell(o[4 * k + 2], invX, C);
+        const int y0 = cull_cell(o[4 * k + 1], invY, C), y1 = cull_cell(o[4 * k + 3], invY, C);
+        for (int y = y0; y <= y1; ++y)
+            for (int x = x0; x <= x1; ++x) {
+                const int at = fill[(size_t)y * C + x]++;
+                memcpy(&items[(size_t)at * 4], &o[4 * k], 16);
+            }
+    }
+    const int startInts = (int)((start.size() + 3) & ~(size_t)3);
+    start.resize(startInts, numItems);
+    if ((size_t)startInts > ctx->cellStartCap) {
+        if (ctx->dCellStart) cudaFree(ctx->dCellStart);
+        CU(cudaMalloc(&ctx->dCellStart, (size_t)startInts * 4));
+        ctx->cellStartCap = startInts;
+    }
+    if ((size_t)std::max(numItems, 1) > ctx->cellItemsCap) {
+        if (ctx->dCellItems) cudaFree(ctx->dCellItems);
+        CU(cudaMalloc(&ctx->dCellItems, (size_t)std::max(numItems, 1) * 16));
+        ctx->cellItemsCap = std::max(numItems, 1);
+    }
+    CU(cudaMemcpyAsync(ctx->dCellStart, start.data(), (size_t)startInts * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (numItems)
+        CU(cudaMemcpyAsync(ctx->dCellItems, items.data(), (size_t)numItems * 16, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));     /* host vectors go out of scope */
+    ctx->cullC = C; ctx->cullInvX = invX; ctx->cullInvY = invY; ctx->cellStartInts = startInts; ctx->numItems = numItems;
+    return KGMT_OK;
+}
+
+static int install_obstacles(kgmt_ctx* ctx) {
+    const int K = ctx->K;
+    if ((size_t)std::max(K, 1) > ctx->obsCap) {
+        if (ctx->dObs) cudaFree(ctx->dObs);
+        CU(cudaMalloc(&ctx->dObs, (size_t)std::max(K, 1) * 16));
+        ctx->obsCap = std::max(K, 1);
+    }
+    if (K) CU(cudaMemcpyAsync(ctx->dObs, ctx->hObs.data(), (size_t)K * 16, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = build_cull_grid(ctx);
+    if (rc) return rc;
+    return configure(ctx);
+}
+
+static int ensure_scratch(kgmt_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->scratchBytes) return KGMT_OK;
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr; ctx->scratchBytes = 0;
+    CU(cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratchBytes = bytes;
+    return KGMT_OK;
+}
+
+static int ensure_record(kgmt_ctx* ctx) {
+    if (ctx->recordAllocated) return KGMT_OK;
+    const size_t M = (size_t)ctx->maxCand;
+    CU(cudaMalloc(&ctx->candState, M * 16));
+    CU(cudaMalloc(&ctx->candCtrl, M * 16));
+    CU(cudaMalloc(&ctx->candParent, M * 4));
+    CU(cudaMalloc(&ctx->candR1, M * 4));
+    CU(cudaMalloc(&ctx->candR2, M * 4));
+    CU(cudaMalloc(&ctx->candFlags, M));
+    ctx->recordAllocated = true;
+    CU(cudaMemsetAsync(ctx->candState, 0, M * 16, ctx->stream));
+    CU(cudaMemsetAsync(ctx->candCtrl, 0, M * 16, ctx->stream));
+    CU(cudaMemsetAsync(ctx->candParent, 0xFF, M * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->candR1, 0xFF, M * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->candR2, 0xFF, M * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->candFlags, 0, M, ctx->stream));
+    return KGMT_OK;
+}
+
+/* state as left by the reference constructor (KGMT.cu:16-40,70-72): zeros, parents -1, scores 1.0.
+ * Only the tree / candidate rows a previous plan touched are rewritten (the rest still is in that state).
+ * Asynchronous on the context's stream; the scalar block is rebuilt on the host. */
+static int clear_state(kgmt_ctx* ctx, bool sync) {
+    const size_t T = std::min((size_t)ctx->p.max_tree_size, ctx->dirtyTree);
+    if (T) {
+        CU(cudaMemsetAsync(ctx->treeState, 0, T * 16, ctx->stream));
+        CU(cudaMemsetAsync(ctx->treeCtrl, 0, T * 16, ctx->stream));
+        CU(cudaMemsetAsync(ctx->treeParent, 0xFF, T * 4, ctx->stream));
+    }
+    CU(cudaMemsetAsync(ctx->mapSlab, 0, ctx->mapSlabInts * 4, ctx->stream));
+    fill_float_kernel<<<(ctx->c1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->R1Score, 1.0f, (size_t)ctx->c1);
+    if (ctx->recordAllocated) {
+        const size_t M = std::min((size_t)ctx->maxCand, ctx->dirtyCand);
+        if (M) {
+            CU(cudaMemsetAsync(ctx->candState, 0, M * 16, ctx->stream));
+            CU(cudaMemsetAsync(ctx->candCtrl, 0, M * 16, ctx->stream));
+            CU(cudaMemsetAsync(ctx->candParent, 0xFF, M * 4, ctx->stream));
+            CU(cudaMemsetAsync(ctx->candR1, 0xFF, M * 4, ctx->stream));
+            CU(cudaMemsetAsync(ctx->candR2, 0xFF, M * 4, ctx->stream));
+            CU(cudaMemsetAsync(ctx->candFlags, 0, M, ctx->stream));
+        }
+    }
+    ctx->dirtyTree = 0; ctx->dirtyCand = 0;
+    /* scalars: keep the scan epoch monotone across resets */
+    DevState z{};
+    z.goalIdx = -1; z.goalBest = ~0ull; z.stop = STOP_ITER_LIMIT;
+    ctx->epochBase += 4096u;
+    z.epoch = ctx->epochBase;
+    z.forceChildren = ctx->hState->forceChildren;
+    ctx->resetState = z;
+    CU(cudaMemcpyAsync(ctx->dState, &ctx->resetState, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
+    if (sync) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        *ctx->hState = z;
+    }
+    ctx->begun = false;
+    ctx->haveCkpt = false;
+    return KGMT_OK;
+}
+
+static int fetch_state(kgmt_ctx* ctx) {
+    CU(cudaMemcpyAsync(ctx->hState, ctx->dState, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->dirtyTree = std::max(ctx->dirtyTree, (size_t)std::max(ctx->hState->treeSize, 0));
+    if (ctx->hState->iterationsDone > 0) ctx->dirtyCand = ctx->maxCand;
+    return KGMT_OK;
+}
+
+static void fill_result(const kgmt_ctx* ctx, kgmt_result* out, float ms) {
+    const DevState& s = *ctx->hState;
+    out->stop = s.stop; out->iterations = s.iterationsDone; out->tree_size = s.treeSize;
+    out->cost_to_goal = s.costToGoal; out->goal_index = s.goalIdx; out->expansions = s.expansions;
+    out->device_ms = ms; out->kernel_launches = ctx->planLaunches;
+}
+
+/* ================================================================================ ABI == */
+extern "C" {
+
+int kgmt_abi_version(void) { return KGMT_ABI_VERSION; }
+
+void kgmt_default_params(kgmt_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->width = 20.0f; p->height = 20.0f; p->N = 16; p->n = 8; p->num_iterations = 100; p->max_tree_size = 30000;
+    p->num_disc = 10; p->agent_length = 1.0f; p->goal_threshold = 0.5f;
+    p->seed = 1u; p->device = -1; p->max_candidates = 0; p->collision_mode = KGMT_COLLIDE_GRID;
+    p->record_candidates = 0; p->cull_cells = 0;
+}
+
+const char* kgmt_last_error(const kgmt_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+void kgmt_destroy(kgmt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->treeState); cudaFree(ctx->treeCtrl); cudaFree(ctx->treeParent);
+    cudaFree(ctx->mapSlab); cudaFree(ctx->mapSlabCkpt);
+    cudaFree(ctx->candState); cudaFree(ctx->candCtrl); cudaFree(ctx->candParent);
+    cudaFree(ctx->candR1); cudaFree(ctx->candR2); cudaFree(ctx->candFlags);
+    cudaFree(ctx->tileStatus); cudaFree(ctx->dState);
+    if (ctx->hState) cudaFreeHost(ctx->hState);
+    cudaFree(ctx->dObs); cudaFree(ctx->dCellStart); cudaFree(ctx->dCellItems);
+    cudaFree(ctx->scratch); cudaFree(ctx->dParents);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int kgmt_create(const kgmt_params* p, kgmt_ctx** out) {
+    if (!p || !out) return KGMT_ERR_INVALID;
+    *out = nullptr;
+    if (!(p->width > 0.f) || !(p->height > 0.f) || p->N < 1 || p->n < 1 || p->max_tree_size < 1 || p->num_disc < 1 ||
+        !(p->agent_length != 0.f) || p->N > 1024 || p->n > 1024)
+        return KGMT_ERR_INVALID;
+    if ((long long)p->N * p->N * p->n * p->n > (1LL << 30)) return KGMT_ERR_INVALID;
+    kgmt_ctx* ctx = new (std::nothrow) kgmt_ctx();
+    if (!ctx) return KGMT_ERR_NOMEM;
+    *out = ctx;                                   /* returned even on failure so the caller can read the error */
+    ctx->p = *p;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(ctx, KGMT_ERR_CUDA, "no CUDA device (%s): this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (p->device >= 0) { ctx->device = p->device; } else { CU(cudaGetDevice(&ctx->device)); }
+    CU(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ctx->device));
+    if (prop.major < 10) return fail(ctx, KGMT_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only",
+                                     prop.name, prop.major, prop.minor);
+    ctx->numSMs = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&ctx->ev0));
+    CU(cudaEventCreate(&ctx->ev1));
+
+    const int N = p->N, n = p->n;
+    ctx->c1 = N * N;
+    ctx->c2 = (size_t)ctx->c1 * n * n;
+    ctx->R1Size = p->width / N;                   /* KGMT.cu:13 */
+    ctx->R2Size = p->width / (n * N);             /* KGMT.cu:14 */
+    ctx->maxCand = p->max_candidates > 0 ? p->max_candidates : p->max_tree_size;
+    ctx->useHist = ((size_t)2 * ctx->c1 * 4 <= 32 * 1024) ? 1 : 0;
+
+    const size_t T = (size_t)p->max_tree_size;
+    CU(cudaMalloc(&ctx->treeState, T * 16));
+    CU(cudaMalloc(&ctx->treeCtrl, T * 16));
+    CU(cudaMalloc(&ctx->treeParent, T * 4));
+    const size_t c1 = (size_t)ctx->c1, c2 = ctx->c2;
+    ctx->mapSlabInts = 6 * c1 + 4 * c2;
+    CU(cudaMalloc(&ctx->mapSlab, ctx->mapSlabInts * 4));
+    int* m = ctx->mapSlab;
+    ctx->R1 = m; m += c1; ctx->R1Valid = m; m += c1; ctx->R1Invalid = m; m += c1; ctx->R1Avail = m; m += c1;
+    ctx->R1Cov = m; m += c1; ctx->R1Score = reinterpret_cast<float*>(m); m += c1;
+    ctx->R2 = m; m += c2; ctx->R2Valid = m; m += c2; ctx->R2Invalid = m; m += c2;
+    ctx->R2Stamp = reinterpret_cast<unsigned*>(m);
+    const size_t tiles = ((size_t)ctx->maxCand + TILE - 1) / TILE + 1;
+    CU(cudaMalloc(&ctx->tileStatus, tiles * 8));
+    CU(cudaMemsetAsync(ctx->tileStatus, 0, tiles * 8, ctx->stream));
+    CU(cudaMalloc(&ctx->dState, sizeof(DevState)));
+    CU(cudaHostAlloc(&ctx->hState, sizeof(DevState), cudaHostAllocDefault));
+    memset(ctx->hState, 0, sizeof(DevState));
+    if (p->record_candidates) { int rc = ensure_record(ctx); if (rc) return rc; }
+    ctx->dirtyTree = T; ctx->dirtyCand = ctx->maxCand;
+    int rc = clear_state(ctx, true);
+    if (rc) return rc;
+    ctx->K = 0; ctx->hObs.clear();
+    return install_obstacles(ctx);
+}
+
+int kgmt_reset(kgmt_ctx* ctx) {
+    if (!ctx) return KGMT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    return clear_state(ctx, true);
+}
+
+/* the Philox key of the next plan (the reference re-seeds every plan() from time(NULL), KGMT.cu:111) */
+int kgmt_set_seed(kgmt_ctx* ctx, uint32_t seed) {
+    if (!ctx) return KGMT_ERR_INVALID;
+    ctx->p.seed = seed;
+    return KGMT_OK;
+}
+
+int kgmt_set_obstacles_host(kgmt_ctx* ctx, const float* h_aabb, int K) {
+    if (!ctx || K < 0 || (K > 0 && !h_aabb)) return fail(ctx, KGMT_ERR_INVALID, "bad obstacle array");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->hObs.assign(h_aabb, h_aabb + (size_t)4 * K);
+    ctx->K = K;
+    return install_obstacles(ctx);
+}
+
+int kgmt_set_obstacles(kgmt_ctx* ctx, const float* d_aabb, int K) {
+    if (!ctx || K < 0 || (K > 0 && !d_aabb)) return fail(ctx, KGMT_ERR_INVALID, "bad obstacle array");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->hObs.resize((size_t)4 * K);
+    if (K) CU(cudaMemcpy(ctx->hObs.data(), d_aabb, (size_t)K * 16, cudaMemcpyDeviceToHost));
+    ctx->K = K;
+    return install_obstacles(ctx);
+}
+
+int kgmt_begin(kgmt_ctx* ctx, const float* initial7, const float* goal7) {
+    if (!ctx || !initial7 || !goal7) return fail(ctx, KGMT_ERR_INVALID, "null initial/goal");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->begun) { int rc = clear_state(ctx, true); if (rc) return rc; }
+    memcpy(ctx->goal, goal7, sizeof(ctx->goal));
+    const KArgs A = make_args(ctx);
+    begin_kernel<<<1, TILE, 0, ctx->stream>>>(A, make_float4(initial7[0], initial7[1], initial7[2], initial7[3]),
+                                             make_float4(initial7[4], initial7[5], initial7[6], 0.f));
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    ctx->planLaunches = 1;
+    ctx->begun = true;
+    return fetch_state(ctx);
+}
+
+static int launch_iteration(kgmt_ctx* ctx) {
+    const KArgs A = make_args(ctx);
+    const bool rec = ctx->p.record_candidates != 0;
+    expand_fn f = expand_entry(ctx->col, false, rec);
+    int grid = std::min(ctx->gridMax, std::max(1, ctx->hState->numTiles));
+    f<<<grid, TILE, ctx->smemBytes, ctx->stream>>>(A);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    ctx->planLaunches += 1;
+    return KGMT_OK;
+}
+
+int kgmt_expand_iteration(kgmt_ctx* ctx, kgmt_iter_stats* out) {
+    if (!ctx) return KGMT_ERR_INVALID;
+    if (!ctx->begun) return fail(ctx, KGMT_ERR_STATE, "kgmt_expand_iteration before kgmt_begin / kgmt_seed_frontier");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->hState->stop == STOP_RUNNING) {
+        int rc = launch_iteration(ctx);
+        if (rc) return rc;
+        rc = fetch_state(ctx);
+        if (rc) return rc;
+    }
+    if (out) {
+        const DevState& s = *ctx->hState;
+        out->iteration = s.lastItr; out->mode = s.lastMode; out->children = s.lastChildren; out->frontier = s.lastFrontier;
+        out->candidates = s.lastM; out->accepted = s.lastAccepted; out->tree_size = s.treeSize; out->stop = s.stop;
+        out->cost_to_goal = s.costToGoal; out->goal_index = s.goalIdx;
+    }
+    return KGMT_OK;
+}
+
+int kgmt_get_result(kgmt_ctx* ctx, kgmt_result* out) {
+    if (!ctx || !out) return KGMT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    int rc = fetch_state(ctx);
+    if (rc) return rc;
+    fill_result(ctx, out, 0.f);
+    return KGMT_OK;
+}
+
+/* KGMT::plan: root insertion + the whole expansion loop in ONE cooperative persistent launch */
+int kgmt_plan(kgmt_ctx* ctx, const float* initial7, const float* goal7, kgmt_result* out) {
+    if (!ctx || !initial7 || !goal7) return fail(ctx, KGMT_ERR_INVALID, "null initial/goal");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (ctx->begun) { int rc = clear_state(ctx, false); if (rc) return rc; }      /* re-plan: inside the timed region */
+    memcpy(ctx->goal, goal7, sizeof(ctx->goal));
+    KArgs A = make_args(ctx);
+    begin_kernel<<<1, TILE, 0, ctx->stream>>>(A, make_float4(initial7[0], initial7[1], initial7[2], initial7[3]),
+                                             make_float4(initial7[4], initial7[5], initial7[6], 0.f));
+    CU(cudaGetLastError());
+    const bool rec = ctx->p.record_candidates != 0;
+    expand_fn f = expand_entry(ctx->col, true, rec);
+    void* args[] = {(void*)&A};
+    CU(cudaLaunchCooperativeKernel((const void*)f, dim3(ctx->gridLoop), dim3(TILE), args, ctx->smemBytes, ctx->stream));
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->launches += 2;
+    ctx->planLaunches = 2;
+    ctx->begun = true;
+    int rc = fetch_state(ctx);
+    if (rc) return rc;
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (out) fill_result(ctx, out, ms);
+    return KGMT_OK;
+}
+
+/* ---- stage-level entry points ------------------------------------------------------------- */
+int kgmt_stage_scores(kgmt_ctx* ctx) {
+    if (!ctx) return KGMT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    const KArgs A = make_args(ctx);
+    recount_cov_kernel<<<ctx->c1, 128, 0, ctx->stream>>>(A);
+    scores_kernel<<<1, TILE, 0, ctx->stream>>>(A);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KGMT_OK;
+}
+
+int kgmt_stage_propagate(kgmt_ctx* ctx, const float* h_parents7, int P, int children, uint32_t key0, uint32_t slot0,
+                         float* device_ms) {
+    if (!ctx || !h_parents7 || P < 1 || children < 1) return fail(ctx, KGMT_ERR_INVALID, "bad parents/children");
+    const long long M = (long long)P * children;
+    if (M > ctx->maxCand) return fail(ctx, KGMT_ERR_INVALID, "P*children = %lld exceeds max_candidates %d", M, ctx->maxCand);
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_record(ctx);
+    if (rc) return rc;
+    if ((size_t)P > ctx->parentsCap) {
+        if (ctx->dParents) cudaFree(ctx->dParents);
+        ctx->dParents = nullptr; ctx->parentsCap = 0;
+        CU(cudaMalloc(&ctx->dParents, (size_t)P * 16));
+        ctx->parentsCap = P;
+    }
+    std::vector<float> st((size_t)P * 4);
+    for (int i = 0; i < P; ++i) memcpy(&st[(size_t)i * 4], &h_parents7[(size_t)i * 7], 16);
+    CU(cudaMemcpyAsync(ctx->dParents, st.data(), (size_t)P * 16, cudaMemcpyHostToDevice, ctx->stream));
+    const KArgs A = make_args(ctx);
+    const size_t smem = ctx->smemBytes - (ctx->useHist ? (((size_t)2 * ctx->c1 * 4 + 15) & ~(size_t)15) : 0);
+    const long long tiles = (M + TILE - 1) / TILE;
+    const int grid = (int)std::min<long long>(tiles, (long long)ctx->gridMax * 4);
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    propagate_entry(ctx->col)<<<grid, TILE, smem, ctx->stream>>>(A, ctx->dParents, M, children, key0, slot0);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->launches += 1;
+    ctx->dirtyCand = ctx->maxCand;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (device_ms) CU(cudaEventElapsedTime(device_ms, ctx->ev0, ctx->ev1));
+    return KGMT_OK;
+}
+
+int kgmt_seed_frontier(kgmt_ctx* ctx, const float* h_nodes7, int count, const float* goal7) {
+    if (!ctx || !h_nodes7 || !goal7 || count < 1 || count > ctx->p.max_tree_size)
+        return fail(ctx, KGMT_ERR_INVALID, "bad frontier");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->begun) { int rc = clear_state(ctx, true); if (rc) return rc; }
+    memcpy(ctx->goal, goal7, sizeof(ctx->goal));
+    int rc = ensure_scratch(ctx, (size_t)count * 28);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->scratch, h_nodes7, (size_t)count * 28, cudaMemcpyHostToDevice, ctx->stream));
+    scatter_samples_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>((const float*)ctx->scratch, ctx->treeState,
+                                                                         ctx->treeCtrl, count);
+    const KArgs A = make_args(ctx);
+    seed_mark_kernel<<<(count + 255) / 256, 256, 0, ctx->stream>>>(A, count);
+    recount_cov_kernel<<<ctx->c1, 128, 0, ctx->stream>>>(A);
+    seed_finish_kernel<<<1, TILE, 0, ctx->stream>>>(A, count);
+    CU(cudaGetLastError());
+    ctx->launches += 4;
+    ctx->planLaunches = 4;
+    ctx->dirtyTree = std::max(ctx->dirtyTree, (size_t)count);
+    ctx->begun = true;
+    return fetch_state(ctx);
+}
+
+/* kgmt_set_children: > 0 forces that many children per frontier node in every later iteration
+ * (throughput sweeps, BASELINE config 5); 0 restores the reference policy (KGMT.cu:151-158). */
+int kgmt_set_children(kgmt_ctx* ctx, int children) {
+    if (!ctx || children < 0) return KGMT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    int rc = fetch_state(ctx);
+    if (rc) return rc;
+    ctx->hState->forceChildren = children;
+    if (ctx->begun && ctx->hState->stop == STOP_RUNNING) {
+        /* re-shape the pending iteration */
+        DevState& s = *ctx->hState;
+        const int remaining = ctx->p.max_tree_size - s.treeSize;
+        if (children > 0) {
+            if ((long long)s.frontierCount * children > std::min<long long>(remaining, ctx->maxCand))
+                return fail(ctx, KGMT_ERR_INVALID, "frontier*children exceeds the remaining tree/candidate capacity");
+            s.mode = 4; s.children = children; s.M = s.frontierCount * children;
+        } else if (32LL * s.frontierCount > remaining) {
+            const int it = (int)((float)remaining / (float)s.frontierCount);
+            if (it >= 1) { s.mode = 2; s.children = it; s.M = s.frontierCount * it; }
+            else { s.mode = 3; s.children = 1; s.M = remaining; }
+        } else { s.mode = 1; s.children = 32; s.M = 32 * s.frontierCount; }
+        s.numTiles = (s.M + TILE - 1) / TILE;
+    }
+    CU(cudaMemcpyAsync(ctx->dState, ctx->hState, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KGMT_OK;
+}
+
+int kgmt_checkpoint(kgmt_ctx* ctx) {
+    if (!ctx) return KGMT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->mapSlabCkpt) CU(cudaMalloc(&ctx->mapSlabCkpt, ctx->mapSlabInts * 4));
+    CU(cudaMemcpyAsync(ctx->mapSlabCkpt, ctx->mapSlab, ctx->mapSlabInts * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    int rc = fetch_state(ctx);
+    if (rc) return rc;
+    ctx->ckptState = *ctx->hState;
+    ctx->haveCkpt = true;
+    return KGMT_OK;
+}
+
+int kgmt_restore(kgmt_ctx* ctx) {
+    if (!ctx) return KGMT_ERR_INVALID;
+    if (!ctx->haveCkpt) return fail(ctx, KGMT_ERR_STATE, "kgmt_restore without kgmt_checkpoint");
+    CU(cudaSetDevice(ctx->device));
+    int rc = fetch_state(ctx);
+    if (rc) return rc;
+    const unsigned epoch = ctx->hState->epoch;
+    CU(cudaMemcpyAsync(ctx->mapSlab, ctx->mapSlabCkpt, ctx->mapSlabInts * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    *ctx->hState = ctx->ckptState;
+    ctx->hState->epoch = epoch + 1u;               /* scan tags stay unique */
+    ctx->hState->ticket = 0; ctx->hState->ctasDone = 0;
+    CU(cudaMemcpyAsync(ctx->dState, ctx->hState, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return KGMT_OK;
+}
+
+/* ---- data exchange -------------------------------------------------------------------------- */
+size_t kgmt_array_bytes(const kgmt_ctx* ctx, int id) {
+    if (!ctx) return 0;
+    const size_t T = (size_t)ctx->p.max_tree_size, M = (size_t)ctx->maxCand, c1 = (size_t)ctx->c1, c2 = ctx->c2;
+    switch (id) {
+        case KGMT_ARR_SAMPLES: return T * 28;
+        case KGMT_ARR_UNEXPLORED: return M * 28;
+        case KGMT_ARR_PARENT: return T * 4;
+        case KGMT_ARR_U_PARENT: return M * 4;
+        case KGMT_ARR_G: return T;
+        case KGMT_ARR_R2AVAIL: case KGMT_ARR_R2VALID: case KGMT_ARR_R2INVALID: case KGMT_ARR_R2: return c2 * 4;
+        case KGMT_ARR_R1AVAIL: case KGMT_ARR_R1VALID: case KGMT_ARR_R1INVALID: case KGMT_ARR_R1SCORE: case KGMT_ARR_R1:
+            return c1 * 4;
+        case KGMT_ARR_COSTS: return T * 4;
+        case KGMT_ARR_U_VALID: case KGMT_ARR_U_ACCEPT: return M;
+        case KGMT_ARR_U_R1: case KGMT_ARR_U_R2: case KGMT_ARR_U_U3: return M * 4;
+        default: return 0;
+    }
+}
+
+int kgmt_export(kgmt_ctx* ctx, int id, void* h_dst, size_t bytes) {
+    if (!ctx || !h_dst) return KGMT_ERR_INVALID;
+    const size_t need = kgmt_array_bytes(ctx, id);
+    if (need == 0) return fail(ctx, KGMT_ERR_INVALID, "unknown array id %d", id);
+    if (bytes < need) return fail(ctx, KGMT_ERR_INVALID, "array %d needs %zu bytes, buffer has %zu", id, need, bytes);
+    CU(cudaSetDevice(ctx->device));
+    const int T = ctx->p.max_tree_size, M = ctx->maxCand;
+    const bool candId = (id == KGMT_ARR_UNEXPLORED || id == KGMT_ARR_U_PARENT || id >= KGMT_ARR_U_VALID);
+    if (candId && !ctx->recordAllocated)
+        return fail(ctx, KGMT_ERR_STATE, "array %d is only kept when record_candidates = 1", id);
+    const void* src = nullptr;
+    cudaStream_t s = ctx->stream;
+    switch (id) {
+        case KGMT_ARR_SAMPLES: {
+            int rc = ensure_scratch(ctx, need); if (rc) return rc;
+            gather_samples_kernel<<<(T + 255) / 256, 256, 0, s>>>(ctx->treeState, ctx->treeCtrl, (float*)ctx->scratch, T, 0);
+            src = ctx->scratch; break; }
+        case KGMT_ARR_UNEXPLORED: {
+            int rc = ensure_scratch(ctx, need); if (rc) return rc;
+            gather_samples_kernel<<<(M + 255) / 256, 256, 0, s>>>(ctx->candState, ctx->candCtrl, (float*)ctx->scratch, M, 1);
+            src = ctx->scratch; break; }
+        case KGMT_ARR_COSTS: {
+            int rc = ensure_scratch(ctx, need); if (rc) return rc;
+            gather_w_kernel<<<(T + 255) / 256, 256, 0, s>>>(ctx->treeCtrl, (float*)ctx->scratch, T);
+            src = ctx->scratch; break; }
+        case KGMT_ARR_U_U3: {
+            int rc = ensure_scratch(ctx, need); if (rc) return rc;
+            gather_w_kernel<<<(M + 255) / 256, 256, 0, s>>>(ctx->candCtrl, (float*)ctx->scratch, M);
+            src = ctx->scratch; break; }
+        case KGMT_ARR_G: {
+            int rc = ensure_scratch(ctx, need); if (rc) return rc;
+            rc = fetch_state(ctx); if (rc) return rc;
+            const bool running = ctx->begun;
+            frontier_flags_kernel<<<(T + 255) / 256, 256, 0, s>>>((unsigned char*)ctx->scratch, T,
+                running ? ctx->hState->frontierStart : 0, running ? ctx->hState->frontierCount : 0);
+            src = ctx->scratch; break; }
+        case KGMT_ARR_R2AVAIL: {
+            int rc = ensure_scratch(ctx, need); if (rc) return rc;
+            stamp_to_avail_kernel<<<(unsigned)((ctx->c2 + 255) / 256), 256, 0, s>>>(ctx->R2Stamp, (int*)ctx->scratch, (int)ctx->c2);
+            src = ctx->scratch; break; }
+        case KGMT_ARR_U_VALID: case KGMT_ARR_U_ACCEPT: {
+            int rc = ensure_scratch(ctx, need); if (rc) return rc;
+            flags_bit_kernel<<<(M + 255) / 256, 256, 0, s>>>(ctx->candFlags, (unsigned char*)ctx->scratch, M,
+                                                            id == KGMT_ARR_U_VALID ? FLAG_VALID : FLAG_ACCEPT);
+            src = ctx->scratch; break; }
+        case KGMT_ARR_PARENT: src = ctx->treeParent; break;
+        case KGMT_ARR_U_PARENT: src = ctx->candParent; break;
+        case KGMT_ARR_R1AVAIL: src = ctx->R1Avail; break;
+        case KGMT_ARR_R1VALID: src = ctx->R1Valid; break;
+        case KGMT_ARR_R2VALID: src = ctx->R2Valid; break;
+        case KGMT_ARR_R1INVALID: src = ctx->R1Invalid; break;
+        case KGMT_ARR_R2INVALID: src = ctx->R2Invalid; break;
+        case KGMT_ARR_R1SCORE: src = ctx->R1Score; break;
+        case KGMT_ARR_R1: src = ctx->R1; break;
+        case KGMT_ARR_R2: src = ctx->R2; break;
+        case KGMT_ARR_U_R1: src = ctx->candR1; break;
+        case KGMT_ARR_U_R2: src = ctx->candR2; break;
+        default: return fail(ctx, KGMT_ERR_INVALID, "unknown array id %d", id);
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h_dst, src, need, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return KGMT_OK;
+}
+
+int kgmt_import(kgmt_ctx* ctx, int id, const void* h_src, size_t bytes) {
+    if (!ctx || !h_src) return KGMT_ERR_INVALID;
+    if (id < KGMT_ARR_R2AVAIL || id > KGMT_ARR_R2) return fail(ctx, KGMT_ERR_INVALID, "only map arrays (5..13) can be imported");
+    const size_t need = kgmt_array_bytes(ctx, id);
+    if (bytes < need) return fail(ctx, KGMT_ERR_INVALID, "array %d needs %zu bytes", id, need);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    void* dst = nullptr;
+    switch (id) {
+        case KGMT_ARR_R2AVAIL: {
+            int rc = ensure_scratch(ctx, need); if (rc) return rc;
+            CU(cudaMemcpyAsync(ctx->scratch, h_src, need, cudaMemcpyHostToDevice, s));
+            avail_to_stamp_kernel<<<(unsigned)((ctx->c2 + 255) / 256), 256, 0, s>>>((const int*)ctx->scratch, ctx->R2Stamp, (int)ctx->c2);
+            const KArgs A = make_args(ctx);
+            recount_cov_kernel<<<ctx->c1, 128, 0, s>>>(A);
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(s));
+            return KGMT_OK; }
+        case KGMT_ARR_R1AVAIL: dst = ctx->R1Avail; break;
+        case KGMT_ARR_R1VALID: dst = ctx->R1Valid; break;
+        case KGMT_ARR_R2VALID: dst = ctx->R2Valid; break;
+        case KGMT_ARR_R1INVALID: dst = ctx->R1Invalid; break;
+        case KGMT_ARR_R2INVALID: dst = ctx->R2Invalid; break;
+        case KGMT_ARR_R1SCORE: dst = ctx->R1Score; break;
+        case KGMT_ARR_R1: dst = ctx->R1; break;
+        case KGMT_ARR_R2: dst = ctx->R2; break;
+        default: return KGMT_ERR_INVALID;
+    }
+    CU(cudaMemcpyAsync(dst, h_src, need, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
+    return KGMT_OK;
+}
+
+/* parent-link back-trace, root first (the reference stops at costToGoal) */
+int kgmt_extract_path(kgmt_ctx* ctx, int node, float* h_rows7, int max_rows) {
+    if (!ctx || max_rows < 0 || (max_rows > 0 && !h_rows7)) return KGMT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    int rc = fetch_state(ctx);
+    if (rc) return rc;
+    const int T = ctx->hState->treeSize;
+    if (node < 0) node = ctx->hState->goalIdx;
+    if (node < 0 || node >= T) return fail(ctx, KGMT_ERR_INVALID, "no such node %d (tree size %d)", node, T);
+    std::vector<int> parent((size_t)T);
+    CU(cudaMemcpyAsync(parent.data(), ctx->treeParent, (size_t)T * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::vector<int> chain;
+    for (int v = node; v >= 0 && (int)chain.size() <= T; v = parent[v]) chain.push_back(v);
+    std::reverse(chain.begin(), chain.end());
+    const int len = (int)chain.size();
+    for (int i = 0; i < len && i < max_rows; ++i) {
+        float4 s, c;
+        CU(cudaMemcpyAsync(&s, ctx->treeState + chain[i], 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(&c, ctx->treeCtrl + chain[i], 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float* r = h_rows7 + (size_t)i * 7;
+        r[0] = s.x; r[1] = s.y; r[2] = s.z; r[3] = s.w; r[4] = c.x; r[5] = c.y; r[6] = c.z;
+    }
+    return len;
+}
+
+/* the reference's 13 CSV dumps, KGMT.cu:299-311, in the format of helper.cuh:53-72 */
+static int write_csv(kgmt_ctx* ctx, const std::string& path, const void* data, int kind, size_t rows, int cols) {
+    FILE* f = fopen(path.c_str(), "w");
+    if (!f) return fail(ctx, KGMT_ERR_INVALID, "cannot open %s", path.c_str());
+    for (size_t i = 0; i < rows; ++i) {
+        for (int j = 0; j < cols; ++j) {
+            const size_t at = i * cols + j;
+            if (kind == 0) fprintf(f, "%.10f", (double)((const float*)data)[at]);
+            else if (kind == 1) fprintf(f, "%d", ((const int*)data)[at]);
+            else fprintf(f, "%d", (int)((const unsigned char*)data)[at]);
+            if (j < cols - 1) fputc(',', f);
+        }
+        fputc('\n', f);
+    }
+    fclose(f);
+    return KGMT_OK;
+}
+
+int kgmt_dump_csv(kgmt_ctx* ctx, const char* dir) {
+    if (!ctx || !dir) return KGMT_ERR_INVALID;
+    struct Item { int id; const char* name; int kind; int cols; };
+    const Item items[13] = {
+        {KGMT_ARR_SAMPLES, "samples.csv", 0, 7}, {KGMT_ARR_UNEXPLORED, "unexploredSamples.csv", 0, 7},
+        {KGMT_ARR_PARENT, "parentRelations.csv", 1, 1}, {KGMT_ARR_U_PARENT, "uParentIdx.csv", 1, 1},
+        {KGMT_ARR_G, "G.csv", 2, 1}, {KGMT_ARR_R2AVAIL, "R2Avail.csv", 1, 1}, {KGMT_ARR_R1AVAIL, "R1Avail.csv", 1, 1},
+        {KGMT_ARR_R1VALID, "R1Valid.csv", 1, 1}, {KGMT_ARR_R2VALID, "R2Valid.csv", 1, 1},
+        {KGMT_ARR_R1INVALID, "R1Invalid.csv", 1, 1}, {KGMT_ARR_R2INVALID, "R2Invalid.csv", 1, 1},
+        {KGMT_ARR_R1SCORE, "R1Score.csv", 0, 1}, {KGMT_ARR_R1, "R1.csv", 1, 1}};
+    std::vector<unsigned char> buf;
+    for (const Item& it : items) {
+        const size_t bytes = kgmt_array_bytes(ctx, it.id);
+        buf.assign(bytes, 0);
+        const bool candId = (it.id == KGMT_ARR_UNEXPLORED || it.id == KGMT_ARR_U_PARENT);
+        if (candId && !ctx->recordAllocated) {
+            if (it.id == KGMT_ARR_U_PARENT) memset(buf.data(), 0xFF, bytes);    /* never-written slots: -1 / 0 as the ctor leaves them */
+        } else {
+            int rc = kgmt_export(ctx, it.id, buf.data(), bytes);
+            if (rc) return rc;
+        }
+        const size_t elem = it.kind == 2 ? 1 : 4;
+        const size_t rows = bytes / (elem * it.cols);
+        int rc = write_csv(ctx, std::string(dir) + "/" + it.name, buf.data(), it.kind, rows, it.cols);
+        if (rc) return rc;
+    }
+    return KGMT_OK;
+}
+
+/* ---- introspection -------------------------------------------------------------------------- */
+int kgmt_tree_size(const kgmt_ctx* ctx) { return ctx ? ctx->hState->treeSize : 0; }
+float kgmt_cost_to_goal(const kgmt_ctx* ctx) { return ctx ? ctx->hState->costToGoal : 0.f; }
+float kgmt_r1_size(const kgmt_ctx* ctx) { return ctx ? ctx->R1Size : 0.f; }
+float kgmt_r2_size(const kgmt_ctx* ctx) { return ctx ? ctx->R2Size : 0.f; }
+void* kgmt_stream(const kgmt_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+long long kgmt_launch_count(const kgmt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+/* what the planner resolved for this obstacle set: collision back end, cull grid, shared memory, grid */
+int kgmt_get_config(const kgmt_ctx* ctx, int* out8) {
+    if (!ctx || !out8) return KGMT_ERR_INVALID;
+    out8[0] = ctx->col; out8[1] = ctx->cullC; out8[2] = ctx->numItems; out8[3] = (int)ctx->smemBytes;
+    out8[4] = ctx->gridLoop; out8[5] = ctx->numSMs; out8[6] = ctx->useHist; out8[7] = ctx->K;
+    return KGMT_OK;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,169 @@
+/* kgmt_device.cuh — per-candidate device arithmetic of the KGMT expansion step.
+ *
+ * Written from scratch for sm_100a.  Every function names the reference lines
+ * whose RESULT it reproduces (paths relative to the reference tree).  The
+ * arithmetic is pinned with explicit round-to-nearest intrinsics so that the
+ * FMA contractions are the ones nvcc applies to the reference itself on
+ * sm_100a (read off its PTX; DESIGN.md "numerical contract"), independent of
+ * compiler flags.  Trigonometry is libdevice's accurate sinf/cosf/tanf — never
+ * compile this file with -use_fast_math.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kgmt {
+
+/* ------------------------------------------------------------------ Philox4x32-10 --
+ * cuRAND's counter-based generator (/usr/local/cuda/include/curand_philox4x32_x.h:88-190),
+ * used statelessly: candidate slot s of iteration itr draws its four uniforms
+ * from Philox(ctr = (0,0,s,0), key = (seed+itr, 0)) — exactly the stream
+ * curand_init(seed+itr, s, 0) + 4x curand_uniform yields for
+ * curandStatePhilox4_32_10_t, i.e. what the reference's initCurandStates
+ * (src/planners/KGMT.cu:595-600) + draws (statePropagator.cu:17-19,
+ * KGMT.cu:395) produce when its curandState is Philox.  No RNG state is stored
+ * (the reference moves 96 B of XORWOW state per candidate, KGMT.cu:386,412). */
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t slot, uint32_t key0) {
+    uint32_t c0 = 0u, c1 = 0u, c2 = slot, c3 = 0u;
+    uint32_t k0 = key0, k1 = 0u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0;
+        const uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+/* curand_uniform: (0,1], /usr/local/cuda/include/curand_uniform.h:69-72 */
+__device__ __forceinline__ float uniform01(uint32_t x) {
+    return __fmaf_rn(__uint2float_rn(x), 2.3283064e-10f, 1.1641532e-10f);
+}
+
+struct Controls { float a, steering, duration, u3; };
+
+/* statePropagator.cu:17-19 (+ the accept uniform of KGMT.cu:395) */
+__device__ __forceinline__ Controls sample_controls(uint32_t slot, uint32_t key0) {
+    const uint4 w = philox4x32_10(slot, key0);
+    const float u0 = uniform01(w.x), u1 = uniform01(w.y), u2 = uniform01(w.z);
+    Controls c;
+    c.a = __fmaf_rn(u0, 10.0f, -5.0f);
+    c.steering = __double2float_rn(__fma_rn((double)__fadd_rn(u1, u1), 3.14159265358979323846, -3.14159265358979323846));
+    c.duration = __fadd_rn(u2, 0.05f);
+    c.u3 = uniform01(w.w);
+    return c;
+}
+
+/* --------------------------------------------------------------------- region index --
+ * getR1 / getR2, src/planners/KGMT.cu:602-629 (== OccupancyGrid::getCellIndex,
+ * src/occupancyMaps/OccupancyGrid.cu:12-19): IEEE division, truncation toward zero. */
+__device__ __forceinline__ int region_r1(float x, float y, float R1Size, int N) {
+    const int cx = __float2int_rz(__fdiv_rn(x, R1Size));
+    const int cy = __float2int_rz(__fdiv_rn(y, R1Size));
+    return (cx >= 0 && cx < N && cy >= 0 && cy < N) ? cy * N + cx : -1;
+}
+__device__ __forceinline__ int region_r2(float x, float y, int r1, float R1Size, int N, float R2Size, int n) {
+    if (r1 < 0) return -1;
+    const int cyR1 = r1 / N, cxR1 = r1 - cyR1 * N;
+    const float lx = __fmaf_rn(-(float)cxR1, R1Size, x);      /* x - cx*R1Size, one FFMA as the reference's SASS */
+    const float ly = __fmaf_rn(-(float)cyR1, R1Size, y);
+    const int cx = __float2int_rz(__fdiv_rn(lx, R2Size));
+    const int cy = __float2int_rz(__fdiv_rn(ly, R2Size));
+    return (cx >= 0 && cx < n && cy >= 0 && cy < n) ? r1 * (n * n) + cy * n + cx : -1;
+}
+
+/* goal test, KGMT.cu:635-638: differences in float, squares/sqrt in double, '<' on the narrowed float */
+__device__ __forceinline__ bool in_goal(float x, float y, float gx, float gy, float r) {
+    const double dx = (double)__fsub_rn(x, gx), dy = (double)__fsub_rn(y, gy);
+    const float dist = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
+    return dist < r;
+}
+
+/* overlap of a step bounding box with one obstacle (minx,miny,maxx,maxy):
+ * !isBroadPhaseValid, src/collisionCheck/collisionCheck.cu:6-14 (strict; touching is free) */
+__device__ __forceinline__ bool aabb_overlap(float bnx, float bny, float bxx, float bxy, const float4 o) {
+    return (bxx > o.x) & (o.z > bnx) & (bxy > o.y) & (o.w > bny);
+}
+
+/* --------------------------------------------------------------- collision back ends --
+ * A back end answers "does this step bbox overlap any obstacle?" — the result of
+ * isMotionValid (collisionCheck.cu:16-28) negated.  Both give the same answer. */
+
+/* every obstacle, shared-memory resident (float4 per obstacle, one broadcast LDS.128 each) */
+struct CollideSmemAll {
+    const float4* obs; int K;
+    __device__ __forceinline__ bool hit(float bnx, float bny, float bxx, float bxy) const {
+        bool h = false;
+        int k = 0;
+        for (; k + 4 <= K; k += 4) {
+            const float4 o0 = obs[k], o1 = obs[k + 1], o2 = obs[k + 2], o3 = obs[k + 3];
+            h = aabb_overlap(bnx, bny, bxx, bxy, o0) | aabb_overlap(bnx, bny, bxx, bxy, o1) |
+                aabb_overlap(bnx, bny, bxx, bxy, o2) | aabb_overlap(bnx, bny, bxx, bxy, o3);
+            if (h) return true;
+        }
+        for (; k < K; ++k) h |= aabb_overlap(bnx, bny, bxx, bxy, obs[k]);
+        return h;
+    }
+};
+
+/* uniform-grid culled: only the obstacles registered in the cells the bbox touches.
+ * cell(x) = clamp(floor(x*inv)) is monotone, obstacles are registered with the same
+ * function, so every obstacle that can overlap the bbox shares a cell with it: the
+ * flag is identical to the exhaustive test. */
+struct CollideGrid {
+    const int* cellStart;      /* [C*C+1] */
+    const float4* items;       /* obstacle AABBs, grouped by cell */
+    int C; float invX, invY;
+    __device__ __forceinline__ int cell(float v, float inv) const {
+        return min(max(__float2int_rd(__fmul_rn(v, inv)), 0), C - 1);
+    }
+    __device__ __forceinline__ bool hit(float bnx, float bny, float bxx, float bxy) const {
+        const int cx0 = cell(bnx, invX), cx1 = cell(bxx, invX), cy0 = cell(bny, invY), cy1 = cell(bxy, invY);
+        for (int cy = cy0; cy <= cy1; ++cy) {
+            for (int cx = cx0; cx <= cx1; ++cx) {
+                const int c = cy * C + cx;
+                const int e = cellStart[c + 1];
+                for (int k = cellStart[c]; k < e; ++k)
+                    if (aabb_overlap(bnx, bny, bxx, bxy, items[k])) return true;
+            }
+        }
+        return false;
+    }
+};
+
+/* ------------------------------------------------------------------------ dynamics --
+ * propagateAndCheck, src/statePropagator/statePropagator.cu:21-75, with the controls
+ * already drawn.  Explicit Euler on the kinematic bicycle; per step: workspace
+ * bounds (:42-45, theta/v NOT advanced when it fires), then theta/v, then the
+ * step bbox (:49-59) against the obstacles (:61-64).  The state at the moment of
+ * exit is returned whether or not the edge is valid (:67-73).  tanf(steering) is
+ * loop-invariant (the reference recomputes it every step, :36). */
+struct DynParams { float W, H, L; int numDisc; };
+
+template <class Collide>
+__device__ __forceinline__ bool propagate_edge(float4& s, const Controls& u, const DynParams& p, const Collide& col) {
+    const float dt = __fdiv_rn(u.duration, (float)p.numDisc);
+    const float tanS = tanf(u.steering);
+    float x = s.x, y = s.y, th = s.z, v = s.w;
+    bool valid = true;
+    for (int i = 0; i < p.numDisc; ++i) {
+        const float px = x, py = y;
+        float sn, cs;
+        sn = sinf(th); cs = cosf(th);
+        x = __fmaf_rn(dt, __fmul_rn(v, cs), x);
+        y = __fmaf_rn(dt, __fmul_rn(v, sn), y);
+        if (x <= 0.0f || x >= p.W || y <= 0.0f || y >= p.H) { valid = false; break; }
+        th = __fmaf_rn(dt, __fmul_rn(__fdiv_rn(v, p.L), tanS), th);
+        v = __fmaf_rn(u.a, dt, v);
+        const float bnx = (px > x) ? x : px, bxx = (px > x) ? px : x;
+        const float bny = (py > y) ? y : py, bxy = (py > y) ? py : y;
+        if (col.hit(bnx, bny, bxx, bxy)) { valid = false; break; }
+    }
+    s = make_float4(x, y, th, v);
+    return valid;
+}
+
+}  // namespace kgmt

@@ -1,0 +1,301 @@
+"""ctypes binding of libkgmt_b200.so (include/kgmt_c.h) — the KGMT tree-expansion path on B200.
+
+This is the Python face of the C ABI; the reference-compatible C++ face is
+cudasbmp_b200/include/planners/KGMT.cuh.  Names follow the reference planner
+(`KGMT(width, height, N, n, numIterations, maxTreeSize, numDisc, agentLength, goalThreshold)`,
+`plan(initial, goal, obstacles)`: /root/reference include/planners/KGMT.cuh:28,31).
+
+There is no CPU fallback: importing works anywhere (so the ABI can be inspected), but any call
+that computes raises KgmtError without the shared library or without a B200.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libkgmt_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM, ERR_COMM = 0, -1, -2, -3, -4, -5
+STOP = {0: "running", 1: "solved", 2: "tree_full", 3: "iter_limit", 4: "frontier_empty"}
+COLLIDE_GRID, COLLIDE_BRUTE = 0, 1
+
+(ARR_SAMPLES, ARR_UNEXPLORED, ARR_PARENT, ARR_U_PARENT, ARR_G, ARR_R2AVAIL, ARR_R1AVAIL, ARR_R1VALID, ARR_R2VALID,
+ ARR_R1INVALID, ARR_R2INVALID, ARR_R1SCORE, ARR_R1, ARR_R2, ARR_COSTS, ARR_U_VALID, ARR_U_R1, ARR_U_R2, ARR_U_U3,
+ ARR_U_ACCEPT) = range(20)
+
+_DTYPE = {ARR_SAMPLES: (np.float32, 7), ARR_UNEXPLORED: (np.float32, 7), ARR_PARENT: (np.int32, 1),
+          ARR_U_PARENT: (np.int32, 1), ARR_G: (np.uint8, 1), ARR_R2AVAIL: (np.int32, 1), ARR_R1AVAIL: (np.int32, 1),
+          ARR_R1VALID: (np.int32, 1), ARR_R2VALID: (np.int32, 1), ARR_R1INVALID: (np.int32, 1),
+          ARR_R2INVALID: (np.int32, 1), ARR_R1SCORE: (np.float32, 1), ARR_R1: (np.int32, 1), ARR_R2: (np.int32, 1),
+          ARR_COSTS: (np.float32, 1), ARR_U_VALID: (np.uint8, 1), ARR_U_R1: (np.int32, 1), ARR_U_R2: (np.int32, 1),
+          ARR_U_U3: (np.float32, 1), ARR_U_ACCEPT: (np.uint8, 1)}
+
+# every symbol include/kgmt_c.h declares
+ABI_SYMBOLS = [
+    "kgmt_abi_version", "kgmt_default_params", "kgmt_create", "kgmt_destroy", "kgmt_last_error", "kgmt_reset", "kgmt_set_seed",
+    "kgmt_set_obstacles", "kgmt_set_obstacles_host", "kgmt_plan", "kgmt_begin", "kgmt_expand_iteration",
+    "kgmt_get_result", "kgmt_extract_path", "kgmt_stage_scores", "kgmt_stage_propagate", "kgmt_seed_frontier",
+    "kgmt_set_children", "kgmt_checkpoint", "kgmt_restore", "kgmt_export", "kgmt_import", "kgmt_array_bytes",
+    "kgmt_dump_csv", "kgmt_tree_size", "kgmt_cost_to_goal", "kgmt_r1_size", "kgmt_r2_size", "kgmt_stream",
+    "kgmt_launch_count", "kgmt_get_config",
+]
+
+
+class KgmtError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("width", C.c_float), ("height", C.c_float), ("N", C.c_int), ("n", C.c_int),
+                ("num_iterations", C.c_int), ("max_tree_size", C.c_int), ("num_disc", C.c_int),
+                ("agent_length", C.c_float), ("goal_threshold", C.c_float), ("seed", C.c_uint32),
+                ("device", C.c_int), ("max_candidates", C.c_int), ("collision_mode", C.c_int),
+                ("record_candidates", C.c_int), ("cull_cells", C.c_int), ("reserved", C.c_int * 5)]
+
+
+class IterStats(C.Structure):
+    _fields_ = [("iteration", C.c_int), ("mode", C.c_int), ("children", C.c_int), ("frontier", C.c_int),
+                ("candidates", C.c_int), ("accepted", C.c_int), ("tree_size", C.c_int), ("stop", C.c_int),
+                ("cost_to_goal", C.c_float), ("goal_index", C.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Result(C.Structure):
+    _fields_ = [("stop", C.c_int), ("iterations", C.c_int), ("tree_size", C.c_int), ("cost_to_goal", C.c_float),
+                ("goal_index", C.c_int), ("expansions", C.c_longlong), ("device_ms", C.c_float),
+                ("kernel_launches", C.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def load():
+    """Load libkgmt_b200.so.  Raises KgmtError (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KgmtError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(make -C cudasbmp_b200/csrc). There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, f32p = C.c_void_p, C.POINTER(C.c_float)
+    L.kgmt_abi_version.restype = C.c_int
+    L.kgmt_default_params.argtypes = [C.POINTER(Params)]
+    L.kgmt_default_params.restype = None
+    L.kgmt_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.kgmt_destroy.argtypes = [vp]
+    L.kgmt_destroy.restype = None
+    L.kgmt_last_error.argtypes = [vp]
+    L.kgmt_last_error.restype = C.c_char_p
+    L.kgmt_reset.argtypes = [vp]
+    L.kgmt_set_seed.argtypes = [vp, C.c_uint32]
+    L.kgmt_set_obstacles.argtypes = [vp, vp, C.c_int]
+    L.kgmt_set_obstacles_host.argtypes = [vp, f32p, C.c_int]
+    L.kgmt_plan.argtypes = [vp, f32p, f32p, C.POINTER(Result)]
+    L.kgmt_begin.argtypes = [vp, f32p, f32p]
+    L.kgmt_expand_iteration.argtypes = [vp, C.POINTER(IterStats)]
+    L.kgmt_get_result.argtypes = [vp, C.POINTER(Result)]
+    L.kgmt_extract_path.argtypes = [vp, C.c_int, f32p, C.c_int]
+    L.kgmt_stage_scores.argtypes = [vp]
+    L.kgmt_stage_propagate.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, f32p]
+    L.kgmt_seed_frontier.argtypes = [vp, f32p, C.c_int, f32p]
+    L.kgmt_set_children.argtypes = [vp, C.c_int]
+    L.kgmt_checkpoint.argtypes = [vp]
+    L.kgmt_restore.argtypes = [vp]
+    L.kgmt_export.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.kgmt_import.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.kgmt_array_bytes.argtypes = [vp, C.c_int]
+    L.kgmt_array_bytes.restype = C.c_size_t
+    L.kgmt_dump_csv.argtypes = [vp, C.c_char_p]
+    L.kgmt_tree_size.argtypes = [vp]
+    L.kgmt_cost_to_goal.argtypes = [vp]
+    L.kgmt_cost_to_goal.restype = C.c_float
+    L.kgmt_r1_size.argtypes = [vp]
+    L.kgmt_r1_size.restype = C.c_float
+    L.kgmt_r2_size.argtypes = [vp]
+    L.kgmt_r2_size.restype = C.c_float
+    L.kgmt_stream.argtypes = [vp]
+    L.kgmt_stream.restype = vp
+    L.kgmt_launch_count.argtypes = [vp]
+    L.kgmt_launch_count.restype = C.c_longlong
+    L.kgmt_get_config.argtypes = [vp, C.POINTER(C.c_int)]
+    _lib = L
+    return L
+
+
+def default_params():
+    p = Params()
+    load().kgmt_default_params(C.byref(p))
+    return p
+
+
+def _f32(a, n=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if n is not None and a.size != n:
+        raise ValueError("expected %d floats, got %d" % (n, a.size))
+    return a
+
+
+class KGMT:
+    """The reference's planner object over the B200 library.
+
+    KGMT(width, height, N, n, numIterations, maxTreeSize, numDisc, agentLength, goalThreshold)
+    mirrors the reference constructor; keyword arguments expose what the reference hard-codes
+    (seed: it uses time(NULL), KGMT.cu:111) or does not have (collision back end, recording).
+    """
+
+    def __init__(self, width=20.0, height=20.0, N=16, n=8, numIterations=100, maxTreeSize=30000, numDisc=10,
+                 agentLength=1.0, goalThreshold=0.5, *, seed=1, device=-1, max_candidates=0,
+                 collision_mode=COLLIDE_GRID, record_candidates=False, cull_cells=0, stage_limit_bytes=0):
+        L = load()
+        p = default_params()
+        p.width, p.height, p.N, p.n = width, height, N, n
+        p.num_iterations, p.max_tree_size, p.num_disc = numIterations, maxTreeSize, numDisc
+        p.agent_length, p.goal_threshold = agentLength, goalThreshold
+        p.seed, p.device, p.max_candidates = seed & 0xFFFFFFFF, device, max_candidates
+        p.collision_mode, p.record_candidates, p.cull_cells = collision_mode, int(bool(record_candidates)), cull_cells
+        p.reserved[0] = stage_limit_bytes
+        self.params = p
+        self.N, self.n, self.max_tree = N, n, maxTreeSize
+        self.max_cand = max_candidates if max_candidates > 0 else maxTreeSize
+        self._h = C.c_void_p()
+        rc = L.kgmt_create(C.byref(p), C.byref(self._h))
+        if rc != OK:
+            msg = L.kgmt_last_error(self._h).decode() if self._h else "invalid parameters"
+            if self._h:
+                L.kgmt_destroy(self._h)
+                self._h = C.c_void_p()
+            raise KgmtError("kgmt_create failed (%d): %s" % (rc, msg))
+        self.R1Size_ = L.kgmt_r1_size(self._h)
+        self.R2Size_ = L.kgmt_r2_size(self._h)
+        self.treeSize_ = 0
+        self.costToGoal_ = 0.0
+
+    # ------------------------------------------------------------------ plumbing
+    def _ck(self, rc):
+        if rc < 0:
+            raise KgmtError("libkgmt_b200 error %d: %s" % (rc, load().kgmt_last_error(self._h).decode()))
+        return rc
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().kgmt_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ reference surface
+    def set_obstacles(self, aabb):
+        """aabb: host float[K][4] (minx, miny, maxx, maxy) — configurations/obstacles/obstacles.csv rows."""
+        a = _f32(aabb).reshape(-1, 4)
+        self._ck(load().kgmt_set_obstacles_host(self._h, a.ctypes.data_as(C.POINTER(C.c_float)), a.shape[0]))
+
+    def set_obstacles_device(self, dptr, K):
+        """dptr: device pointer (int) to float[K][4], as KGMT::plan's d_obstacles."""
+        self._ck(load().kgmt_set_obstacles(self._h, C.c_void_p(int(dptr)), int(K)))
+
+    def plan(self, initial, goal, obstacles=None):
+        """KGMT::plan (KGMT.cu:80-317): returns the result dict; treeSize_/costToGoal_ as the reference members."""
+        if obstacles is not None:
+            self.set_obstacles(obstacles)
+        i, g = _f32(initial, 7), _f32(goal, 7)
+        r = Result()
+        f32p = C.POINTER(C.c_float)
+        self._ck(load().kgmt_plan(self._h, i.ctypes.data_as(f32p), g.ctypes.data_as(f32p), C.byref(r)))
+        self.treeSize_, self.costToGoal_ = r.tree_size, r.cost_to_goal
+        return r.as_dict()
+
+    # ------------------------------------------------------------------ stepwise
+    def begin(self, initial, goal):
+        i, g = _f32(initial, 7), _f32(goal, 7)
+        f32p = C.POINTER(C.c_float)
+        self._ck(load().kgmt_begin(self._h, i.ctypes.data_as(f32p), g.ctypes.data_as(f32p)))
+
+    def iterate(self):
+        s = IterStats()
+        self._ck(load().kgmt_expand_iteration(self._h, C.byref(s)))
+        self.treeSize_, self.costToGoal_ = s.tree_size, s.cost_to_goal
+        return s.as_dict()
+
+    def result(self):
+        r = Result()
+        self._ck(load().kgmt_get_result(self._h, C.byref(r)))
+        return r.as_dict()
+
+    def reset(self):
+        self._ck(load().kgmt_reset(self._h))
+
+    def set_seed(self, seed):
+        self._ck(load().kgmt_set_seed(self._h, int(seed) & 0xFFFFFFFF))
+
+    def seed_frontier(self, nodes7, goal):
+        a = _f32(nodes7).reshape(-1, 7)
+        g = _f32(goal, 7)
+        f32p = C.POINTER(C.c_float)
+        self._ck(load().kgmt_seed_frontier(self._h, a.ctypes.data_as(f32p), a.shape[0], g.ctypes.data_as(f32p)))
+
+    def set_children(self, children):
+        self._ck(load().kgmt_set_children(self._h, int(children)))
+
+    def checkpoint(self):
+        self._ck(load().kgmt_checkpoint(self._h))
+
+    def restore(self):
+        self._ck(load().kgmt_restore(self._h))
+
+    def stage_scores(self):
+        self._ck(load().kgmt_stage_scores(self._h))
+
+    def stage_propagate(self, parents7, children, key0, slot0=0):
+        """Stages 2-4 on explicit parents.  Returns device milliseconds; results via export()."""
+        a = _f32(parents7).reshape(-1, 7)
+        ms = C.c_float()
+        self._ck(load().kgmt_stage_propagate(self._h, a.ctypes.data_as(C.POINTER(C.c_float)), a.shape[0], int(children),
+                                             int(key0) & 0xFFFFFFFF, int(slot0) & 0xFFFFFFFF, C.byref(ms)))
+        return ms.value
+
+    def extract_path(self, node=-1, max_rows=4096):
+        buf = np.zeros((max_rows, 7), dtype=np.float32)
+        n = self._ck(load().kgmt_extract_path(self._h, int(node), buf.ctypes.data_as(C.POINTER(C.c_float)), max_rows))
+        return buf[:min(n, max_rows)].copy()
+
+    # ------------------------------------------------------------------ data
+    def export(self, array_id):
+        dt, cols = _DTYPE[array_id]
+        nbytes = load().kgmt_array_bytes(self._h, array_id)
+        out = np.zeros(nbytes // np.dtype(dt).itemsize, dtype=dt)
+        self._ck(load().kgmt_export(self._h, array_id, out.ctypes.data_as(C.c_void_p), nbytes))
+        return out.reshape(-1, cols) if cols > 1 else out
+
+    def import_(self, array_id, values):
+        dt, _ = _DTYPE[array_id]
+        a = np.ascontiguousarray(values, dtype=dt)
+        self._ck(load().kgmt_import(self._h, array_id, a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    def dump_csv(self, directory):
+        os.makedirs(directory, exist_ok=True)
+        self._ck(load().kgmt_dump_csv(self._h, directory.encode()))
+
+    def config(self):
+        out = (C.c_int * 8)()
+        self._ck(load().kgmt_get_config(self._h, out))
+        keys = ("collide_backend", "cull_cells", "cull_items", "smem_bytes", "grid", "sms", "r1_hist", "K")
+        return dict(zip(keys, list(out)))
+
+    @property
+    def launch_count(self):
+        return load().kgmt_launch_count(self._h)
+
+    @property
+    def stream(self):
+        return load().kgmt_stream(self._h)

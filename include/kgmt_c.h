@@ -1,0 +1,191 @@
+/* kgmt_c.h — C ABI of libkgmt_b200.so: the KGMT tree-expansion hot path of
+ * nipe1783/cudaSBMP, written from scratch for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer: its boundary
+ * is the C++ class `KGMT` (include/planners/KGMT.cuh:23-109) constructed and
+ * called by demos/main.cu:30,62.  Every entry point below names the reference
+ * interface it replaces.  The reference-compatible C++ facade
+ * (cudasbmp_b200/include/planners/KGMT.cuh) is a thin header over this ABI, so
+ * demos/main.cu compiles and runs unchanged against it.
+ *
+ * Conventions: plain C types only; every function returns KGMT_OK (0) or a
+ * negative kgmt_status; nothing calls exit() or throws across the boundary
+ * (the reference printf+exit(1)s, include/helper/helper.cuh:19-27); a context
+ * is owned by the caller, bound to one CUDA device and one stream, not
+ * thread-safe; distinct contexts are independent.  There is NO CPU fallback:
+ * without a CUDA device kgmt_create fails with KGMT_ERR_CUDA.
+ */
+#ifndef KGMT_C_H
+#define KGMT_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGMT_ABI_VERSION 1
+#define KGMT_SAMPLE_DIM 7            /* (x, y, theta, v, a, steering, duration): KGMT.cu:5, State.h:9-20 */
+
+typedef enum kgmt_status {
+    KGMT_OK = 0,
+    KGMT_ERR_INVALID = -1,           /* bad argument */
+    KGMT_ERR_CUDA = -2,              /* CUDA runtime error; see kgmt_last_error */
+    KGMT_ERR_STATE = -3,             /* call out of order (e.g. iterate before begin) */
+    KGMT_ERR_NOMEM = -4,
+    KGMT_ERR_COMM = -5               /* NCCL error */
+} kgmt_status;
+
+/* why a plan stopped (KGMT.cu:118,252-259; canonical: SURVEY.md App. B #11) */
+typedef enum kgmt_stop {
+    KGMT_RUNNING = 0,
+    KGMT_SOLVED = 1,                 /* costToGoal != 0                      KGMT.cu:252 */
+    KGMT_TREE_FULL = 2,              /* treeSize >= maxTreeSize              KGMT.cu:255 */
+    KGMT_ITER_LIMIT = 3,             /* itr == numIterations                 KGMT.cu:118 */
+    KGMT_FRONTIER_EMPTY = 4          /* nothing accepted: the reference spins to numIterations */
+} kgmt_stop;
+
+typedef enum kgmt_collide {
+    KGMT_COLLIDE_GRID = 0,           /* uniform-grid culled; same flags as brute force, fewer tests */
+    KGMT_COLLIDE_BRUTE = 1           /* every step bbox vs every obstacle (collisionCheck.cu:16-28), smem tiles */
+} kgmt_collide;
+
+/* The nine constructor arguments of KGMT::KGMT (KGMT.cuh:28, KGMT.cu:10-11) plus
+ * what the reference hard-codes or leaves to chance. */
+typedef struct kgmt_params {
+    float    width, height;          /* workspace                              main.cu:20-21 */
+    int      N, n;                   /* R1 grid N x N, R2 grid n x n per cell  main.cu:22-23 */
+    int      num_iterations;         /*                                        main.cu:24    */
+    int      max_tree_size;          /*                                        main.cu:25    */
+    int      num_disc;               /* Euler steps per edge                   main.cu:26    */
+    float    agent_length;           /* wheelbase L                            main.cu:27    */
+    float    goal_threshold;         /* goal disc radius                       main.cu:28    */
+    uint32_t seed;                   /* Philox key; iteration i uses key (seed+i, 0). Reference: time(NULL), KGMT.cu:111 */
+    int      device;                 /* CUDA ordinal, -1 = current device */
+    int      max_candidates;         /* candidate slots per iteration; 0 = max_tree_size (as the reference, KGMT.cu:28) */
+    int      collision_mode;         /* kgmt_collide */
+    int      record_candidates;      /* 1: also keep per-candidate valid/r1/r2/u3/accept arrays for export */
+    int      cull_cells;             /* cull grid is cull_cells x cull_cells; 0 = choose from the obstacle set */
+    int      reserved[5];            /* [0]: shared-memory staging budget for the cull grid in bytes (0 = 48 KB); rest 0 */
+} kgmt_params;
+
+typedef struct kgmt_iter_stats {
+    int       iteration;             /* 1-based index of the step just executed */
+    int       mode;                  /* 1 = 32 children/node (propagateG), 2 = floor(remaining/active) (propagateGV2), 3 = prefix */
+    int       children;
+    int       frontier;              /* nodes expanded */
+    int       candidates;            /* edges propagated and collision-checked */
+    int       accepted;              /* nodes inserted */
+    int       tree_size;             /* after insertion */
+    int       stop;                  /* kgmt_stop */
+    float     cost_to_goal;
+    int       goal_index;
+} kgmt_iter_stats;
+
+typedef struct kgmt_result {
+    int       stop;                  /* kgmt_stop */
+    int       iterations;
+    int       tree_size;             /* KGMT::treeSize_ */
+    float     cost_to_goal;          /* KGMT::costToGoal_ (0 = none) */
+    int       goal_index;            /* tree index of the goal node, -1 = none */
+    long long expansions;            /* candidate edges checked over the whole plan */
+    float     device_ms;             /* CUDA-event time of the expansion loop */
+    int       kernel_launches;       /* launches of this library's kernels inside the loop */
+} kgmt_result;
+
+/* Array ids for kgmt_export / kgmt_import.  0..12 are the thirteen CSV dumps of
+ * KGMT.cu:299-311, in that order, in the reference's own element layout
+ * (AoS rows of 7 floats, int, bool-as-uint8).  Row counts: max_tree_size for
+ * tree/candidate arrays, N*N for R1*, N*N*n*n for R2*. */
+typedef enum kgmt_array {
+    KGMT_ARR_SAMPLES = 0,            /* float [maxTree][7]   samples.csv            d_treeSamples_      */
+    KGMT_ARR_UNEXPLORED = 1,         /* float [maxCand][7]   unexploredSamples.csv  d_unexploredSamples_*/
+    KGMT_ARR_PARENT = 2,             /* int   [maxTree]      parentRelations.csv    d_treeParentIdx_    */
+    KGMT_ARR_U_PARENT = 3,           /* int   [maxCand]      uParentIdx.csv         d_uParentIdx_       */
+    KGMT_ARR_G = 4,                  /* u8    [maxTree]      G.csv                  d_G_                */
+    KGMT_ARR_R2AVAIL = 5,            /* int   [N*N*n*n]      R2Avail.csv */
+    KGMT_ARR_R1AVAIL = 6,            /* int   [N*N]          R1Avail.csv */
+    KGMT_ARR_R1VALID = 7,
+    KGMT_ARR_R2VALID = 8,
+    KGMT_ARR_R1INVALID = 9,
+    KGMT_ARR_R2INVALID = 10,
+    KGMT_ARR_R1SCORE = 11,           /* float [N*N]          R1Score.csv */
+    KGMT_ARR_R1 = 12,
+    KGMT_ARR_R2 = 13,                /* int   [N*N*n*n]      d_R2_ (not dumped by the reference) */
+    KGMT_ARR_COSTS = 14,             /* float [maxTree]      d_costs_ */
+    /* per-candidate records of the last iteration (record_candidates = 1), [maxCand] */
+    KGMT_ARR_U_VALID = 15,           /* u8    */
+    KGMT_ARR_U_R1 = 16,              /* int   */
+    KGMT_ARR_U_R2 = 17,              /* int   */
+    KGMT_ARR_U_U3 = 18,              /* float accept uniform (KGMT.cu:395) */
+    KGMT_ARR_U_ACCEPT = 19,          /* u8    GNew as decided this iteration (KGMT.cu:397) */
+    KGMT_ARR_COUNT = 20
+} kgmt_array;
+
+typedef struct kgmt_ctx kgmt_ctx;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int  kgmt_abi_version(void);
+void kgmt_default_params(kgmt_params* p);                       /* main.cu:19-28 literals */
+int  kgmt_create(const kgmt_params* p, kgmt_ctx** out);         /* replaces KGMT::KGMT, KGMT.cu:10-78 */
+void kgmt_destroy(kgmt_ctx* ctx);                               /* replaces ~KGMT + KGMT.cu:314-316 */
+const char* kgmt_last_error(const kgmt_ctx* ctx);               /* replaces CUDA_ERROR_CHECK's printf, helper.cuh:19-27 */
+int  kgmt_set_seed(kgmt_ctx* ctx, uint32_t seed);               /* Philox key of the next plan (reference: time(NULL), KGMT.cu:111) */
+int  kgmt_reset(kgmt_ctx* ctx);                                 /* re-plan without re-allocating (reference: single-shot, App. B #12) */
+
+/* ---- obstacles: float[K][4] = (minx, miny, maxx, maxy), obstacles.csv:1-5 ------------------ */
+int  kgmt_set_obstacles(kgmt_ctx* ctx, const float* d_aabb, int K);      /* DEVICE pointer, as plan()'s d_obstacles (KGMT.cuh:31, main.cu:60-62); copied */
+int  kgmt_set_obstacles_host(kgmt_ctx* ctx, const float* h_aabb, int K); /* HOST pointer (what readObstaclesFromCSV returns, helper.cu:11-34) */
+
+/* ---- planning ------------------------------------------------------------------------------ */
+/* KGMT::plan (KGMT.cuh:31, KGMT.cu:80-317) without the CSV dump: initial/goal are HOST float[7]. */
+int  kgmt_plan(kgmt_ctx* ctx, const float* initial7, const float* goal7, kgmt_result* out);
+/* the same, split: root insertion (KGMT.cu:85-114) then one while-loop body (KGMT.cu:118-259) per call */
+int  kgmt_begin(kgmt_ctx* ctx, const float* initial7, const float* goal7);
+int  kgmt_expand_iteration(kgmt_ctx* ctx, kgmt_iter_stats* out);
+int  kgmt_get_result(kgmt_ctx* ctx, kgmt_result* out);
+/* back-trace of the parent links from the goal node (or any node) to the root: rows of 7 floats,
+ * root first.  Returns the path length (may exceed max_rows; only max_rows are written). */
+int  kgmt_extract_path(kgmt_ctx* ctx, int node, float* h_rows7, int max_rows);
+
+/* ---- stage-level entry points (parity tests, throughput sweeps) ----------------------------- */
+/* Stage 1: R1 scores from the current maps (updateR1, KGMT.cu:487-538). */
+int  kgmt_stage_scores(kgmt_ctx* ctx);
+/* Stages 2-4 only: candidate s (0 <= s < P*children) expands h_parents7[s / children] with stream
+ * (key0, slot0 + s); fills the candidate arrays (UNEXPLORED, U_VALID, U_R1, U_R2, U_U3); maps and tree untouched.
+ * (propagateAndCheck, statePropagator.cu:5-76 + getR1/getR2, KGMT.cu:602-629) */
+int  kgmt_stage_propagate(kgmt_ctx* ctx, const float* h_parents7, int P, int children,
+                          uint32_t key0, uint32_t slot0, float* device_ms);
+/* Load `count` nodes (HOST rows of 7 floats) as tree[0,count), all of them frontier, costs 0, root cells
+ * marked like KGMT.cu:88-97 for every node; then kgmt_expand_iteration steps from there. */
+int  kgmt_seed_frontier(kgmt_ctx* ctx, const float* h_nodes7, int count, const float* goal7);
+/* > 0: that many children per frontier node in every later iteration (throughput sweeps, BASELINE config 5);
+ * 0: the reference policy (32, or floor(remaining/active) when the tree is nearly full, KGMT.cu:151-158) */
+int  kgmt_set_children(kgmt_ctx* ctx, int children);
+/* device-side checkpoint / restore of maps + scalars (tree rows above the checkpointed size are dead) */
+int  kgmt_checkpoint(kgmt_ctx* ctx);
+int  kgmt_restore(kgmt_ctx* ctx);
+
+/* ---- data exchange -------------------------------------------------------------------------- */
+int  kgmt_export(kgmt_ctx* ctx, int array_id, void* h_dst, size_t bytes);        /* copyAndWriteVectorToCSV's D2H half, helper.cuh:74-79 */
+int  kgmt_import(kgmt_ctx* ctx, int array_id, const void* h_src, size_t bytes);  /* maps only (ids 5..13) */
+size_t kgmt_array_bytes(const kgmt_ctx* ctx, int array_id);
+/* the reference's 13 CSV files (KGMT.cu:299-311, "%.10f" fixed, helper.cuh:53-72) into `dir` */
+int  kgmt_dump_csv(kgmt_ctx* ctx, const char* dir);
+
+/* ---- introspection -------------------------------------------------------------------------- */
+int  kgmt_tree_size(const kgmt_ctx* ctx);
+float kgmt_cost_to_goal(const kgmt_ctx* ctx);
+float kgmt_r1_size(const kgmt_ctx* ctx);                         /* KGMT::R1Size_, KGMT.cu:13 */
+float kgmt_r2_size(const kgmt_ctx* ctx);                         /* KGMT::R2Size_, KGMT.cu:14 */
+void* kgmt_stream(const kgmt_ctx* ctx);                          /* cudaStream_t the context launches on */
+long long kgmt_launch_count(const kgmt_ctx* ctx);                /* kernels of this library launched so far */
+/* out8 = {collision back end (0 grid/smem, 1 grid/L1, 2 exhaustive/smem, 3 exhaustive/L1), cull cells per side,
+ *         cull grid items, dynamic shared memory bytes, persistent grid size, SM count, R1 smem histograms, K} */
+int  kgmt_get_config(const kgmt_ctx* ctx, int* out8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGMT_C_H */

@@ -221,6 +221,28 @@ int orc_getR2(float x, float y, int r1, float R1Size, int N, float R2Size, int n
     return -1;
 }
 
+/* The same function as nvcc/ptxas build it for sm_100a: `x - cell*R1Size` is
+ * contracted into one FFMA (read off the SASS of the reference's KGMT.o:
+ * `FFMA R40, R40, -R7, R5`).  Identical to orc_getR2 whenever cell*R1Size is
+ * exactly representable (all shipped configurations: R1Size = 1.25). */
+int orc_getR2_fma(float x, float y, int r1, float R1Size, int N, float R2Size, int n) {
+    if (r1 == -1) return -1;
+    int cellY_R1 = r1 / N;
+    int cellX_R1 = r1 % N;
+    float localX = fmaf(-(float)cellX_R1, R1Size, x);
+    float localY = fmaf(-(float)cellY_R1, R1Size, y);
+    int cellX_R2 = (int)(localX / R2Size);
+    int cellY_R2 = (int)(localY / R2Size);
+    if (cellX_R2 >= 0 && cellX_R2 < n && cellY_R2 >= 0 && cellY_R2 < n)
+        return r1 * (n * n) + cellY_R2 * n + cellX_R2;
+    return -1;
+}
+
+int orc_getR2_mode(float x, float y, int r1, float R1Size, int N, float R2Size, int n, int math_mode) {
+    return math_mode == ORC_MATH_FMA ? orc_getR2_fma(x, y, r1, R1Size, N, R2Size, n)
+                                     : orc_getR2(x, y, r1, R1Size, N, R2Size, n);
+}
+
 /* ---------------------------------------------------------------- scores -- */
 /* src/planners/KGMT.cu:500-537, for any N (canonical: App. B #9).
  *   covR    = (# available R2 cells of the R1 cell) / n^2           (:510-514)
@@ -375,7 +397,7 @@ void orc_begin(orc_planner* p, const float initial[7], const float goal[7]) {
     memcpy(p->treeSamples, initial, 7 * sizeof(float));               /* :85 */
     p->G[0] = 1;                                                       /* :86-87 */
     int r1 = orc_getR1(initial[0], initial[1], p->R1Size, p->N);      /* :88 */
-    int r2 = orc_getR2(initial[0], initial[1], r1, p->R1Size, p->N, p->R2Size, p->n); /* :89 */
+    int r2 = orc_getR2_mode(initial[0], initial[1], r1, p->R1Size, p->N, p->R2Size, p->n, p->math_mode); /* :89 */
     if (r1 >= 0) { p->R1[r1] = 1; p->R1Avail[r1] = 1; p->R1Valid[r1] = 1; }  /* :94,95,97 */
     if (r2 >= 0) p->R2Avail[r2] = 1;                                   /* :96 */
     memcpy(p->xGoal, goal, 7 * sizeof(float));                         /* :101 */
@@ -490,7 +512,7 @@ int orc_iterate(orc_planner* p) {
                                     p->width, p->height, p->math_mode, x1, &p->uU3[s],
                                     &p->uMargin[s], NULL);
         p->uR1[s] = orc_getR1(x1[0], x1[1], p->R1Size, p->N);         /* :390 */
-        p->uR2[s] = orc_getR2(x1[0], x1[1], p->uR1[s], p->R1Size, p->N, p->R2Size, p->n); /* :391 */
+        p->uR2[s] = orc_getR2_mode(x1[0], x1[1], p->uR1[s], p->R1Size, p->N, p->R2Size, p->n, p->math_mode); /* :391 */
     }
     p->expansions += M;
 
@@ -570,6 +592,16 @@ void* orc_array(orc_planner* p, int id) {
 }
 
 /* ------------------------------------------------- batch helpers (bench) -- */
+/* region indices of M points (rows of `stride` floats, x at [0], y at [1]) */
+void orc_regions_batch(const float* xy, int stride, long M, float R1Size, int N, float R2Size, int n,
+                       int math_mode, int* r1, int* r2) {
+    for (long s = 0; s < M; ++s) {
+        const float x = xy[(size_t)s * stride], y = xy[(size_t)s * stride + 1];
+        r1[s] = orc_getR1(x, y, R1Size, N);
+        r2[s] = orc_getR2_mode(x, y, r1[s], R1Size, N, R2Size, n, math_mode);
+    }
+}
+
 /* M candidates, candidate s expands parents[parentOf[s]] (rows of 7 floats)
  * with stream (key0, slot0+s).  Any output pointer may be NULL. */
 void orc_propagate_batch(const float* parents, const int* parentOf, long M,

@@ -47,6 +47,8 @@ int   orc_propagate_slot(const float x0[4], uint32_t key0, uint32_t slot, int nu
                          float x1[7], float* u3_out, float* margin, int* steps);
 int   orc_getR1(float x, float y, float R1Size, int N);
 int   orc_getR2(float x, float y, int r1, float R1Size, int N, float R2Size, int n);
+int   orc_getR2_fma(float x, float y, int r1, float R1Size, int N, float R2Size, int n);
+int   orc_getR2_mode(float x, float y, int r1, float R1Size, int N, float R2Size, int n, int math_mode);
 void  orc_scores(const int* R1Avail, const int* R2Avail, const int* R1Valid, const int* R1Invalid,
                  const int* R1, int N, int n, float epsilon, float* R1Score, float* R1Threshold);
 int   orc_in_goal(const float* x, const float* goal, float r);
@@ -84,6 +86,8 @@ int   orc_last_children(const orc_planner* p);
 float orc_R1Threshold(const orc_planner* p);
 void* orc_array(orc_planner* p, int id);
 
+void  orc_regions_batch(const float* xy, int stride, long M, float R1Size, int N, float R2Size, int n,
+                        int math_mode, int* r1, int* r2);
 void  orc_propagate_batch(const float* parents, const int* parentOf, long M,
                           float* x1, uint8_t* valid, float* u3, float* margin,
                           int numDisc, float L, uint32_t key0, uint32_t slot0,

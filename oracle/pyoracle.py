@@ -90,6 +90,11 @@ def lib():
         L.orc_propagate_batch.restype = None
         L.orc_propagate_batch.argtypes = [f32p, i32p, C.c_long, f32p, u8p, f32p, f32p, C.c_int, C.c_float,
                                           C.c_uint32, C.c_uint32, f32p, C.c_int, C.c_float, C.c_float, C.c_int]
+        L.orc_getR2_fma.restype = C.c_int
+        L.orc_getR2_fma.argtypes = [C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int]
+        L.orc_regions_batch.restype = None
+        L.orc_regions_batch.argtypes = [f32p, C.c_int, C.c_long, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int,
+                                        i32p, i32p]
         L.orc_scores.restype = None
         L.orc_scores.argtypes = [i32p, i32p, i32p, i32p, i32p, C.c_int, C.c_int, C.c_float, f32p, f32p]
         L.orc_update_maps.restype = None
@@ -130,6 +135,35 @@ def getR1(x, y, R1Size, N):
 
 def getR2(x, y, r1, R1Size, N, R2Size, n):
     return lib().orc_getR2(float(x), float(y), int(r1), float(R1Size), int(N), float(R2Size), int(n))
+
+
+def getR2_fma(x, y, r1, R1Size, N, R2Size, n):
+    return lib().orc_getR2_fma(float(x), float(y), int(r1), float(R1Size), int(N), float(R2Size), int(n))
+
+
+def regions_batch(rows, R1Size, N, R2Size, n, math_mode=MATH_FMA):
+    """rows: float32 [M, stride>=2] with x, y in the first two columns.  Returns (r1[M], r2[M])."""
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    M, stride = rows.shape
+    r1 = np.zeros(M, dtype=np.int32)
+    r2 = np.zeros(M, dtype=np.int32)
+    lib().orc_regions_batch(_p(rows, f32p), stride, M, float(R1Size), int(N), float(R2Size), int(n), math_mode,
+                            _p(r1, i32p), _p(r2, i32p))
+    return r1, r2
+
+
+def insert(accept, cand7, cand_parent, tree_size, tree7, tree_parent, costs, G, goal7, r, cost_to_goal=0.0, goal_idx=-1):
+    """orc_insert on numpy arrays (tree arrays updated in place).  Returns (accepted, costToGoal, goalIdx)."""
+    accept = np.ascontiguousarray(accept, dtype=np.uint8)
+    cand7 = np.ascontiguousarray(cand7, dtype=np.float32)
+    cand_parent = np.ascontiguousarray(cand_parent, dtype=np.int32)
+    goal7 = np.ascontiguousarray(goal7, dtype=np.float32)
+    ctg = C.c_float(cost_to_goal)
+    gi = C.c_int(goal_idx)
+    k = lib().orc_insert(len(accept), _p(accept, u8p), _p(cand7, f32p), _p(cand_parent, i32p), int(tree_size),
+                         _p(tree7, f32p), _p(tree_parent, i32p), _p(costs, f32p), _p(G, u8p), _p(goal7, f32p), float(r),
+                         C.byref(ctg), C.byref(gi))
+    return k, ctg.value, gi.value
 
 
 def expansion_shape(active, tree_size, max_tree):
