@@ -42,6 +42,7 @@ struct kgmt_ctx {
     unsigned char* candFlags = nullptr;
     bool recordAllocated = false;
     unsigned long long* tileStatus = nullptr;
+    unsigned long long* iterLog = nullptr;
     DevState* dState = nullptr;
     DevState* hState = nullptr;        /* pinned */
     DevState ckptState{};
@@ -124,6 +125,7 @@ static KArgs make_args(const kgmt_ctx* c) {
     A.cellStart = c->dCellStart; A.cellItems = c->dCellItems; A.cullC = c->cullC;
     A.cullInvX = c->cullInvX; A.cullInvY = c->cullInvY; A.cellStartInts = c->cellStartInts; A.numItems = c->numItems;
     A.obsTile = 0;
+    A.iterLog = c->iterLog;
     A.W = c->p.width; A.H = c->p.height; A.L = c->p.agent_length; A.R1Size = c->R1Size; A.R2Size = c->R2Size;
     A.goalX = c->goal[0]; A.goalY = c->goal[1]; A.goalR = c->p.goal_threshold;
     A.N = c->p.N; A.n = c->p.n; A.c1 = c->c1; A.numDisc = c->p.num_disc; A.maxTree = c->p.max_tree_size;
@@ -340,7 +342,7 @@ void kgmt_destroy(kgmt_ctx* ctx) {
     cudaFree(ctx->mapSlab); cudaFree(ctx->mapSlabCkpt);
     cudaFree(ctx->candState); cudaFree(ctx->candCtrl); cudaFree(ctx->candParent);
     cudaFree(ctx->candR1); cudaFree(ctx->candR2); cudaFree(ctx->candFlags);
-    cudaFree(ctx->tileStatus); cudaFree(ctx->dState);
+    cudaFree(ctx->tileStatus); cudaFree(ctx->dState); cudaFree(ctx->iterLog);
     if (ctx->hState) cudaFreeHost(ctx->hState);
     cudaFree(ctx->dObs); cudaFree(ctx->dCellStart); cudaFree(ctx->dCellItems);
     cudaFree(ctx->scratch); cudaFree(ctx->dParents);
@@ -848,6 +850,27 @@ float kgmt_r1_size(const kgmt_ctx* ctx) { return ctx ? ctx->R1Size : 0.f; }
 float kgmt_r2_size(const kgmt_ctx* ctx) { return ctx ? ctx->R2Size : 0.f; }
 void* kgmt_stream(const kgmt_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 long long kgmt_launch_count(const kgmt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+/* per-iteration device timestamps of the last plan (diagnostics): out[i] = {ns since the first logged iteration
+ * ended... raw globaltimer ns, candidates, accepted}; returns the number of rows written (<= max_rows) */
+int kgmt_iteration_log(kgmt_ctx* ctx, int enable, unsigned long long* out3, int max_rows) {
+    if (!ctx) return KGMT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (enable && !ctx->iterLog) {
+        CU(cudaMalloc(&ctx->iterLog, 256 * 16));
+        CU(cudaMemset(ctx->iterLog, 0, 256 * 16));
+    }
+    if (!out3 || max_rows <= 0 || !ctx->iterLog) return 0;
+    int rc = fetch_state(ctx);
+    if (rc) return rc;
+    unsigned long long raw[512];
+    CU(cudaMemcpy(raw, ctx->iterLog, sizeof(raw), cudaMemcpyDeviceToHost));
+    int n = std::min(std::min(ctx->hState->iterationsDone, 255), max_rows);
+    for (int i = 0; i < n; ++i) {
+        out3[3 * i] = raw[2 * i]; out3[3 * i + 1] = raw[2 * i + 1] >> 32; out3[3 * i + 2] = raw[2 * i + 1] & 0xFFFFFFFFull;
+    }
+    return n;
+}
 
 /* what the planner resolved for this obstacle set: collision back end, cull grid, shared memory, grid */
 int kgmt_get_config(const kgmt_ctx* ctx, int* out8) {

@@ -66,6 +66,7 @@ struct KArgs {
     const float4* obstacles; int K;
     const int* cellStart; const float4* cellItems; int cullC; float cullInvX, cullInvY; int cellStartInts; int numItems;
     int obsTile;                  /* obstacles per shared-memory tile (stream mode) */
+    unsigned long long* iterLog;  /* [256][2]: (globaltimer ns, M<<32 | accepted) per finished iteration; null = off */
     /* parameters */
     float W, H, L, R1Size, R2Size, goalX, goalY, goalR;
     int N, n, c1, numDisc, maxTree, numIterations, useHist;
@@ -182,6 +183,12 @@ __device__ void finalize_iteration(const KArgs& A, float* p) {
         const int accepted = (int)(unsigned)ld_relaxed_u64(&A.tileStatus[numTiles - 1]);   /* inclusive total */
         st->lastMode = st->mode; st->lastChildren = st->children; st->lastFrontier = st->frontierCount;
         st->lastM = M; st->lastAccepted = accepted; st->lastItr = st->itr;
+        if (A.iterLog && st->iterationsDone < 255) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            A.iterLog[2 * st->iterationsDone] = t;
+            A.iterLog[2 * st->iterationsDone + 1] = ((unsigned long long)(unsigned)M << 32) | (unsigned)accepted;
+        }
         st->iterationsDone += 1;
         st->expansions += M;
         st->frontierStart = st->treeSize;

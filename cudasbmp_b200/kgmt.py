@@ -38,7 +38,7 @@ ABI_SYMBOLS = [
     "kgmt_get_result", "kgmt_extract_path", "kgmt_stage_scores", "kgmt_stage_propagate", "kgmt_seed_frontier",
     "kgmt_set_children", "kgmt_checkpoint", "kgmt_restore", "kgmt_export", "kgmt_import", "kgmt_array_bytes",
     "kgmt_dump_csv", "kgmt_tree_size", "kgmt_cost_to_goal", "kgmt_r1_size", "kgmt_r2_size", "kgmt_stream",
-    "kgmt_launch_count", "kgmt_get_config",
+    "kgmt_launch_count", "kgmt_get_config", "kgmt_iteration_log",
 ]
 
 
@@ -125,6 +125,7 @@ def load():
     L.kgmt_launch_count.argtypes = [vp]
     L.kgmt_launch_count.restype = C.c_longlong
     L.kgmt_get_config.argtypes = [vp, C.POINTER(C.c_int)]
+    L.kgmt_iteration_log.argtypes = [vp, C.c_int, C.POINTER(C.c_ulonglong), C.c_int]
     _lib = L
     return L
 
@@ -291,6 +292,13 @@ class KGMT:
         self._ck(load().kgmt_get_config(self._h, out))
         keys = ("collide_backend", "cull_cells", "cull_items", "smem_bytes", "grid", "sms", "r1_hist", "K")
         return dict(zip(keys, list(out)))
+
+    def iteration_log(self, enable=True):
+        """Rows (t_ns since the first row, candidates, accepted) of the last plan; call once with enable to switch on."""
+        buf = (C.c_ulonglong * (3 * 256))()
+        n = self._ck(load().kgmt_iteration_log(self._h, int(enable), buf, 256))
+        a = np.array(list(buf), dtype=np.uint64).reshape(-1, 3)[:n]
+        return a
 
     @property
     def launch_count(self):

@@ -1,0 +1,31 @@
+"""Per-iteration device timeline of one plan + a sweep over cull-grid resolution / staging."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from cudasbmp_b200 import kgmt as K, workloads as w
+
+def run(cfg, obs, init, goal, reps=5, **kw):
+    p = K.KGMT(**cfg, seed=1, **kw); p.set_obstacles(obs)
+    p.iteration_log(True)
+    ms = []
+    for s in range(reps):
+        p.set_seed(1 + s); r = p.plan(init, goal); ms.append(r["device_ms"])
+    return p, r, ms
+
+cfg, obs = w.C2, w.c2_obstacles(1000)
+p, r, ms = run(cfg, obs, w.C2_INIT, w.C2_GOAL)
+log = p.iteration_log()
+print("plan", r, "ms", ms)
+t = log[:, 0].astype(np.int64); dt = np.diff(t, prepend=t[0])
+for i, row in enumerate(log):
+    print("itr %2d  M %8d acc %7d  dt %8.1f us" % (i + 1, row[1], row[2], dt[i] / 1e3))
+print("---- sweep")
+for cull in (16, 32, 48, 64, 96, 128):
+    for lim in (48 * 1024, 200 * 1024, 1):
+        try:
+            p, r, ms = run(cfg, obs, w.C2_INIT, w.C2_GOAL, cull_cells=cull, stage_limit_bytes=lim)
+            print("cull %3d lim %6d -> %s  exp %d  ms %s" % (cull, lim, p.config(), r["expansions"], ["%.3f" % m for m in ms]))
+        except Exception as e:
+            print("cull", cull, lim, "failed", e)
+p, r, ms = run(cfg, obs, w.C2_INIT, w.C2_GOAL, collision_mode=K.COLLIDE_BRUTE)
+print("brute", p.config(), r["expansions"], ms)

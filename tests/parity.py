@@ -33,11 +33,14 @@ def export_maps(plan):
     return m
 
 
-def ill_conditioned(x1):
-    """Edges whose heading rate is so large (steering within ~1 degree of +-pi/2, tan > 50) that one ulp of
-    tanf/sinf/cosf is amplified beyond any fixed tolerance; they are checked bit-exactly against the
-    reference's own CUDA kernels instead (test_bit_exact_against_reference_cuda_kernels)."""
-    return np.abs(np.tan(x1[:, 5].astype(np.float64))) > 50.0
+def state_tolerance(x1, theta0, nd):
+    """Per-candidate relative tolerance on the propagated state: TOL_REL per integration step (north_star),
+    scaled by the heading swept over the edge.  sinf/cosf/tanf of libdevice and glibc differ by <= 1-2 ulp; an
+    edge that turns through D radians (steering near +-pi/2: tan up to 1e7) amplifies one ulp of tanf by D, so
+    no fixed tolerance can hold for it.  Those edges are ALSO checked bit for bit against the reference's own
+    CUDA kernels (test_bit_exact_against_reference_cuda_kernels)."""
+    swept = np.abs(x1[:, 2].astype(np.float64) - np.asarray(theta0, dtype=np.float64))
+    return TOL_REL * nd * np.maximum(1.0, swept)
 
 
 def bits(a):
@@ -86,8 +89,7 @@ def check_iteration(plan, po, obstacles, cfg, goal, seed, report=None):
     assert (bits(cand[:, 4:7]) == bits(xo[:, 4:7])).all(), "sampled controls differ"
     assert (bits(u3) == bits(u3o)).all(), "accept uniforms differ"
     err = np.abs(cand[:, :4].astype(np.float64) - xo[:, :4]) / np.maximum(1.0, np.abs(xo[:, :4]))
-    off = (valid != vo) | (err.max(axis=1) > TOL_REL * nd)
-    off &= ~ill_conditioned(xo)
+    off = (valid != vo) | (err.max(axis=1) > state_tolerance(xo, tree0[upar, 2], nd))
     assert (margin[off] <= MARGIN).all(), \
         "propagated state / flag differs away from any boundary: %d candidates, worst margin %g" % (
             int(off.sum()), float(margin[off].max()))

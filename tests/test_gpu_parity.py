@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 from cudasbmp_b200 import kgmt as K          # noqa: E402
 from cudasbmp_b200 import workloads as w     # noqa: E402
-from tests.parity import MARGIN, TOL_REL, bits, check_iteration, ill_conditioned   # noqa: E402
+from tests.parity import MARGIN, TOL_REL, bits, check_iteration, state_tolerance   # noqa: E402
 
 
 def _plan(cfg, obstacles, **kw):
@@ -44,13 +44,15 @@ def test_propagate_against_reference_golden(golden_dir, oracle, name, mode):
     plan = _plan(cfg, g["obstacles"], collision_mode=mode, record_candidates=True)
     x1, valid, u3, _, _ = _propagate(plan, parents, children, int(g["key"]), M)
     assert (bits(u3) == bits(g["u3"])).all()
-    # controls: a and duration are FMA-insensitive; steering differs by the double-precision FMA at most 1 ulp
-    assert (bits(x1[:, 4]) == bits(g["x1"][:, 4])).all() and (bits(x1[:, 6]) == bits(g["x1"][:, 6])).all()
+    # controls: duration has no contraction; a (u*10-5) and steering (u*2*pi-pi) are one FMA on the GPU, two
+    # roundings in the host build: at most 1 ulp of 5 / of pi apart
+    assert (bits(x1[:, 6]) == bits(g["x1"][:, 6])).all()
+    assert np.abs(x1[:, 4] - g["x1"][:, 4]).max() <= 5e-7
     assert np.abs(x1[:, 5] - g["x1"][:, 5]).max() <= 5e-7
     _, _, _, margin = oracle.propagate_batch(parents, pof, int(g["key"]), 0, nd, 1.0, g["obstacles"], 20.0, 20.0,
                                              oracle.MATH_HOST)
     err = np.abs(x1[:, :4].astype(np.float64) - g["x1"][:, :4]) / np.maximum(1.0, np.abs(g["x1"][:, :4]))
-    off = ((valid != g["valid"]) | (err.max(axis=1) > TOL_REL * nd)) & ~ill_conditioned(g["x1"])
+    off = (valid != g["valid"]) | (err.max(axis=1) > state_tolerance(g["x1"], parents[pof, 2], nd))
     assert (margin[off] <= MARGIN).all(), (int(off.sum()), float(margin[off].max()))
     assert off.mean() <= 0.01
 
