@@ -34,14 +34,15 @@ struct kgmt_ctx {
     int* mapSlabCkpt = nullptr;
     size_t mapSlabInts = 0;
     int *R1 = nullptr, *R1Valid = nullptr, *R1Invalid = nullptr, *R1Avail = nullptr, *R1Cov = nullptr;
-    float* R1Score = nullptr;
+    float* R1Score[2] = {nullptr, nullptr};
     int *R2 = nullptr, *R2Valid = nullptr, *R2Invalid = nullptr;
     unsigned* R2Stamp = nullptr;
     float4 *candState = nullptr, *candCtrl = nullptr;
     int *candParent = nullptr, *candR1 = nullptr, *candR2 = nullptr;
     unsigned char* candFlags = nullptr;
     bool recordAllocated = false;
-    unsigned long long* tileStatus = nullptr;
+    unsigned* chunkMask = nullptr; int* blockSum = nullptr; size_t numBlocksCap = 0;
+    float4 *stageState = nullptr, *stageCtrl = nullptr;
     unsigned long long* iterLog = nullptr;
     DevState* dState = nullptr;
     DevState* hState = nullptr;        /* pinned */
@@ -89,17 +90,16 @@ static int fail(kgmt_ctx* c, int code, const char* fmt, ...) {
 static const size_t MAX_DYN_SMEM = 227u * 1024u - 8u * 1024u;   /* leave room for static shared + reserve */
 
 /* -------------------------------------------------------------------------------- kernels table */
-typedef void (*expand_fn)(const KArgs);
-template <int COL> static expand_fn pick_expand(bool loop, bool rec) {
-    if (loop) return rec ? (expand_fn)expand_kernel<COL, true, true> : (expand_fn)expand_kernel<COL, true, false>;
-    return rec ? (expand_fn)expand_kernel<COL, false, true> : (expand_fn)expand_kernel<COL, false, false>;
+typedef void (*expand_fn)(const KArgs, int);
+template <int COL> static expand_fn pick_expand(bool rec) {
+    return rec ? (expand_fn)expand_kernel<COL, true> : (expand_fn)expand_kernel<COL, false>;
 }
-static expand_fn expand_entry(int col, bool loop, bool rec) {
+static expand_fn expand_entry(int col, bool rec) {
     switch (col) {
-        case COL_GRID_SMEM: return pick_expand<COL_GRID_SMEM>(loop, rec);
-        case COL_GRID_GLOBAL: return pick_expand<COL_GRID_GLOBAL>(loop, rec);
-        case COL_BRUTE_SMEM: return pick_expand<COL_BRUTE_SMEM>(loop, rec);
-        default: return pick_expand<COL_BRUTE_GLOBAL>(loop, rec);
+        case COL_GRID_SMEM: return pick_expand<COL_GRID_SMEM>(rec);
+        case COL_GRID_GLOBAL: return pick_expand<COL_GRID_GLOBAL>(rec);
+        case COL_BRUTE_SMEM: return pick_expand<COL_BRUTE_SMEM>(rec);
+        default: return pick_expand<COL_BRUTE_GLOBAL>(rec);
     }
 }
 typedef void (*prop_fn)(const KArgs, const float4*, long long, int, uint32_t, uint32_t);
@@ -116,11 +116,12 @@ static KArgs make_args(const kgmt_ctx* c) {
     KArgs A{};
     A.treeState = c->treeState; A.treeCtrl = c->treeCtrl; A.treeParent = c->treeParent;
     A.R1 = c->R1; A.R1Valid = c->R1Valid; A.R1Invalid = c->R1Invalid; A.R1Avail = c->R1Avail; A.R1Cov = c->R1Cov;
-    A.R1Score = c->R1Score;
+    A.R1Score[0] = c->R1Score[0]; A.R1Score[1] = c->R1Score[1];
     A.R2 = c->R2; A.R2Valid = c->R2Valid; A.R2Invalid = c->R2Invalid; A.R2Stamp = c->R2Stamp;
     A.candState = c->candState; A.candCtrl = c->candCtrl; A.candParent = c->candParent;
     A.candR1 = c->candR1; A.candR2 = c->candR2; A.candFlags = c->candFlags;
-    A.tileStatus = c->tileStatus; A.st = c->dState;
+    A.chunkMask = c->chunkMask; A.blockSum = c->blockSum; A.stageState = c->stageState; A.stageCtrl = c->stageCtrl;
+    A.st = c->dState;
     A.obstacles = c->dObs; A.K = c->K;
     A.cellStart = c->dCellStart; A.cellItems = c->dCellItems; A.cullC = c->cullC;
     A.cullInvX = c->cullInvX; A.cullInvY = c->cullInvY; A.cellStartInts = c->cellStartInts; A.numItems = c->numItems;
@@ -150,15 +151,14 @@ static int configure(kgmt_ctx* ctx) {
     if (col == COL_GRID_GLOBAL || col == COL_BRUTE_GLOBAL) colBytes = 0;
     ctx->col = col;
     ctx->smemBytes = histBytes + colBytes;
-    int occ = 0;
-    for (int loop = 0; loop < 2; ++loop)
-        for (int rec = 0; rec < 2; ++rec) {
-            expand_fn f = expand_entry(col, loop, rec);
-            CU(cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemBytes));
-            int o = 0;
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void*)f, TILE, ctx->smemBytes));
-            if (loop == 1 && rec == (ctx->p.record_candidates ? 1 : 0)) occ = o;
-        }
+    int occ = 1 << 30;
+    for (int rec = 0; rec < 2; ++rec) {
+        expand_fn f = expand_entry(col, rec != 0);
+        CU(cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemBytes));
+        int o = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void*)f, TILE, ctx->smemBytes));
+        occ = std::min(occ, o);
+    }
     CU(cudaFuncSetAttribute((const void*)propagate_entry(col), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)colBytes));
     if (occ < 1) return fail(ctx, KGMT_ERR_CUDA, "expand kernel does not fit on an SM (smem %zu B)", ctx->smemBytes);
     ctx->gridLoop = occ * ctx->numSMs;
@@ -273,7 +273,8 @@ static int clear_state(kgmt_ctx* ctx, bool sync) {
         CU(cudaMemsetAsync(ctx->treeParent, 0xFF, T * 4, ctx->stream));
     }
     CU(cudaMemsetAsync(ctx->mapSlab, 0, ctx->mapSlabInts * 4, ctx->stream));
-    fill_float_kernel<<<(ctx->c1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->R1Score, 1.0f, (size_t)ctx->c1);
+    CU(cudaMemsetAsync(ctx->blockSum, 0, ctx->numBlocksCap * 4, ctx->stream));
+    fill_float_kernel<<<(2 * ctx->c1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->R1Score[0], 1.0f, (size_t)2 * ctx->c1);
     if (ctx->recordAllocated) {
         const size_t M = std::min((size_t)ctx->maxCand, ctx->dirtyCand);
         if (M) {
@@ -289,8 +290,6 @@ static int clear_state(kgmt_ctx* ctx, bool sync) {
     /* scalars: keep the scan epoch monotone across resets */
     DevState z{};
     z.goalIdx = -1; z.goalBest = ~0ull; z.stop = STOP_ITER_LIMIT;
-    ctx->epochBase += 4096u;
-    z.epoch = ctx->epochBase;
     z.forceChildren = ctx->hState->forceChildren;
     ctx->resetState = z;
     CU(cudaMemcpyAsync(ctx->dState, &ctx->resetState, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
@@ -342,7 +341,8 @@ void kgmt_destroy(kgmt_ctx* ctx) {
     cudaFree(ctx->mapSlab); cudaFree(ctx->mapSlabCkpt);
     cudaFree(ctx->candState); cudaFree(ctx->candCtrl); cudaFree(ctx->candParent);
     cudaFree(ctx->candR1); cudaFree(ctx->candR2); cudaFree(ctx->candFlags);
-    cudaFree(ctx->tileStatus); cudaFree(ctx->dState); cudaFree(ctx->iterLog);
+    cudaFree(ctx->chunkMask); cudaFree(ctx->blockSum); cudaFree(ctx->stageState); cudaFree(ctx->stageCtrl);
+    cudaFree(ctx->dState); cudaFree(ctx->iterLog);
     if (ctx->hState) cudaFreeHost(ctx->hState);
     cudaFree(ctx->dObs); cudaFree(ctx->dCellStart); cudaFree(ctx->dCellItems);
     cudaFree(ctx->scratch); cudaFree(ctx->dParents);
@@ -392,16 +392,21 @@ int kgmt_create(const kgmt_params* p, kgmt_ctx** out) {
     CU(cudaMalloc(&ctx->treeCtrl, T * 16));
     CU(cudaMalloc(&ctx->treeParent, T * 4));
     const size_t c1 = (size_t)ctx->c1, c2 = ctx->c2;
-    ctx->mapSlabInts = 6 * c1 + 4 * c2;
+    ctx->mapSlabInts = 7 * c1 + 4 * c2;
     CU(cudaMalloc(&ctx->mapSlab, ctx->mapSlabInts * 4));
     int* m = ctx->mapSlab;
     ctx->R1 = m; m += c1; ctx->R1Valid = m; m += c1; ctx->R1Invalid = m; m += c1; ctx->R1Avail = m; m += c1;
-    ctx->R1Cov = m; m += c1; ctx->R1Score = reinterpret_cast<float*>(m); m += c1;
+    ctx->R1Cov = m; m += c1; ctx->R1Score[0] = reinterpret_cast<float*>(m); m += c1;
+    ctx->R1Score[1] = reinterpret_cast<float*>(m); m += c1;
     ctx->R2 = m; m += c2; ctx->R2Valid = m; m += c2; ctx->R2Invalid = m; m += c2;
     ctx->R2Stamp = reinterpret_cast<unsigned*>(m);
-    const size_t tiles = ((size_t)ctx->maxCand + TILE - 1) / TILE + 1;
-    CU(cudaMalloc(&ctx->tileStatus, tiles * 8));
-    CU(cudaMemsetAsync(ctx->tileStatus, 0, tiles * 8, ctx->stream));
+    const size_t chunks = ((size_t)ctx->maxCand + CHUNK - 1) / CHUNK + 1;
+    ctx->numBlocksCap = (chunks + BLK_CHUNKS - 1) / BLK_CHUNKS + 1;
+    CU(cudaMalloc(&ctx->chunkMask, chunks * 4));
+    CU(cudaMalloc(&ctx->blockSum, ctx->numBlocksCap * 4));
+    CU(cudaMalloc(&ctx->stageState, (size_t)ctx->maxCand * 16));
+    CU(cudaMalloc(&ctx->stageCtrl, (size_t)ctx->maxCand * 16));
+    CU(cudaMemsetAsync(ctx->chunkMask, 0, chunks * 4, ctx->stream));
     CU(cudaMalloc(&ctx->dState, sizeof(DevState)));
     CU(cudaHostAlloc(&ctx->hState, sizeof(DevState), cudaHostAllocDefault));
     memset(ctx->hState, 0, sizeof(DevState));
@@ -460,13 +465,11 @@ int kgmt_begin(kgmt_ctx* ctx, const float* initial7, const float* goal7) {
     return fetch_state(ctx);
 }
 
-static int launch_iteration(kgmt_ctx* ctx) {
-    const KArgs A = make_args(ctx);
-    const bool rec = ctx->p.record_candidates != 0;
-    expand_fn f = expand_entry(ctx->col, false, rec);
-    int grid = std::min(ctx->gridMax, std::max(1, ctx->hState->numTiles));
-    f<<<grid, TILE, ctx->smemBytes, ctx->stream>>>(A);
-    CU(cudaGetLastError());
+static int launch_expand(kgmt_ctx* ctx, int maxIters) {
+    KArgs A = make_args(ctx);
+    expand_fn f = expand_entry(ctx->col, ctx->p.record_candidates != 0);
+    void* args[] = {(void*)&A, (void*)&maxIters};
+    CU(cudaLaunchCooperativeKernel((const void*)f, dim3(ctx->gridLoop), dim3(TILE), args, ctx->smemBytes, ctx->stream));
     ctx->launches += 1;
     ctx->planLaunches += 1;
     return KGMT_OK;
@@ -477,7 +480,7 @@ int kgmt_expand_iteration(kgmt_ctx* ctx, kgmt_iter_stats* out) {
     if (!ctx->begun) return fail(ctx, KGMT_ERR_STATE, "kgmt_expand_iteration before kgmt_begin / kgmt_seed_frontier");
     CU(cudaSetDevice(ctx->device));
     if (ctx->hState->stop == STOP_RUNNING) {
-        int rc = launch_iteration(ctx);
+        int rc = launch_expand(ctx, 1);
         if (rc) return rc;
         rc = fetch_state(ctx);
         if (rc) return rc;
@@ -511,13 +514,10 @@ int kgmt_plan(kgmt_ctx* ctx, const float* initial7, const float* goal7, kgmt_res
     begin_kernel<<<1, TILE, 0, ctx->stream>>>(A, make_float4(initial7[0], initial7[1], initial7[2], initial7[3]),
                                              make_float4(initial7[4], initial7[5], initial7[6], 0.f));
     CU(cudaGetLastError());
-    const bool rec = ctx->p.record_candidates != 0;
-    expand_fn f = expand_entry(ctx->col, true, rec);
-    void* args[] = {(void*)&A};
-    CU(cudaLaunchCooperativeKernel((const void*)f, dim3(ctx->gridLoop), dim3(TILE), args, ctx->smemBytes, ctx->stream));
+    ctx->launches += 1;
+    ctx->planLaunches = 1;
+    { int rc = launch_expand(ctx, 0x7fffffff); if (rc) return rc; }
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->launches += 2;
-    ctx->planLaunches = 2;
     ctx->begun = true;
     int rc = fetch_state(ctx);
     if (rc) return rc;
@@ -616,7 +616,7 @@ int kgmt_set_children(kgmt_ctx* ctx, int children) {
             if (it >= 1) { s.mode = 2; s.children = it; s.M = s.frontierCount * it; }
             else { s.mode = 3; s.children = 1; s.M = remaining; }
         } else { s.mode = 1; s.children = 32; s.M = 32 * s.frontierCount; }
-        s.numTiles = (s.M + TILE - 1) / TILE;
+        s.numChunks = (s.M + CHUNK - 1) / CHUNK;
     }
     CU(cudaMemcpyAsync(ctx->dState, ctx->hState, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -641,10 +641,8 @@ int kgmt_restore(kgmt_ctx* ctx) {
     CU(cudaSetDevice(ctx->device));
     int rc = fetch_state(ctx);
     if (rc) return rc;
-    const unsigned epoch = ctx->hState->epoch;
     CU(cudaMemcpyAsync(ctx->mapSlab, ctx->mapSlabCkpt, ctx->mapSlabInts * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     *ctx->hState = ctx->ckptState;
-    ctx->hState->epoch = epoch + 1u;               /* scan tags stay unique */
     ctx->hState->ticket = 0; ctx->hState->ctasDone = 0;
     CU(cudaMemcpyAsync(ctx->dState, ctx->hState, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -723,7 +721,7 @@ int kgmt_export(kgmt_ctx* ctx, int id, void* h_dst, size_t bytes) {
         case KGMT_ARR_R2VALID: src = ctx->R2Valid; break;
         case KGMT_ARR_R1INVALID: src = ctx->R1Invalid; break;
         case KGMT_ARR_R2INVALID: src = ctx->R2Invalid; break;
-        case KGMT_ARR_R1SCORE: src = ctx->R1Score; break;
+        case KGMT_ARR_R1SCORE: { int rc = fetch_state(ctx); if (rc) return rc; src = ctx->R1Score[ctx->hState->scoreSel & 1]; break; }
         case KGMT_ARR_R1: src = ctx->R1; break;
         case KGMT_ARR_R2: src = ctx->R2; break;
         case KGMT_ARR_U_R1: src = ctx->candR1; break;
@@ -759,7 +757,7 @@ int kgmt_import(kgmt_ctx* ctx, int id, const void* h_src, size_t bytes) {
         case KGMT_ARR_R2VALID: dst = ctx->R2Valid; break;
         case KGMT_ARR_R1INVALID: dst = ctx->R1Invalid; break;
         case KGMT_ARR_R2INVALID: dst = ctx->R2Invalid; break;
-        case KGMT_ARR_R1SCORE: dst = ctx->R1Score; break;
+        case KGMT_ARR_R1SCORE: { int rc = fetch_state(ctx); if (rc) return rc; dst = ctx->R1Score[ctx->hState->scoreSel & 1]; break; }
         case KGMT_ARR_R1: dst = ctx->R1; break;
         case KGMT_ARR_R2: dst = ctx->R2; break;
         default: return KGMT_ERR_INVALID;
@@ -853,22 +851,18 @@ long long kgmt_launch_count(const kgmt_ctx* ctx) { return ctx ? ctx->launches : 
 
 /* per-iteration device timestamps of the last plan (diagnostics): out[i] = {ns since the first logged iteration
  * ended... raw globaltimer ns, candidates, accepted}; returns the number of rows written (<= max_rows) */
-int kgmt_iteration_log(kgmt_ctx* ctx, int enable, unsigned long long* out3, int max_rows) {
+int kgmt_iteration_log(kgmt_ctx* ctx, int enable, unsigned long long* out8, int max_rows) {
     if (!ctx) return KGMT_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
     if (enable && !ctx->iterLog) {
-        CU(cudaMalloc(&ctx->iterLog, 256 * 16));
-        CU(cudaMemset(ctx->iterLog, 0, 256 * 16));
+        CU(cudaMalloc(&ctx->iterLog, 256 * 64));
+        CU(cudaMemset(ctx->iterLog, 0, 256 * 64));
     }
-    if (!out3 || max_rows <= 0 || !ctx->iterLog) return 0;
+    if (!out8 || max_rows <= 0 || !ctx->iterLog) return 0;
     int rc = fetch_state(ctx);
     if (rc) return rc;
-    unsigned long long raw[512];
-    CU(cudaMemcpy(raw, ctx->iterLog, sizeof(raw), cudaMemcpyDeviceToHost));
-    int n = std::min(std::min(ctx->hState->iterationsDone, 255), max_rows);
-    for (int i = 0; i < n; ++i) {
-        out3[3 * i] = raw[2 * i]; out3[3 * i + 1] = raw[2 * i + 1] >> 32; out3[3 * i + 2] = raw[2 * i + 1] & 0xFFFFFFFFull;
-    }
+    const int n = std::min(std::min(ctx->hState->iterationsDone, 255), max_rows);
+    CU(cudaMemcpy(out8, ctx->iterLog, (size_t)n * 64, cudaMemcpyDeviceToHost));
     return n;
 }
 

@@ -90,12 +90,16 @@ __device__ __forceinline__ bool aabb_overlap(float bnx, float bny, float bxx, fl
 
 /* --------------------------------------------------------------- collision back ends --
  * A back end answers "does this step bbox overlap any obstacle?" — the result of
- * isMotionValid (collisionCheck.cu:16-28) negated.  Both give the same answer. */
+ * isMotionValid (collisionCheck.cu:16-28) negated.  Both give the same answer.
+ * start(x, y) is called once with the edge's first point, hit(...) once per step with the
+ * new point and the step bbox. */
 
 /* every obstacle, shared-memory resident (float4 per obstacle, one broadcast LDS.128 each) */
 struct CollideSmemAll {
     const float4* obs; int K;
-    __device__ __forceinline__ bool hit(float bnx, float bny, float bxx, float bxy) const {
+    struct Cursor {};
+    __device__ __forceinline__ Cursor start(float, float) const { return Cursor{}; }
+    __device__ __forceinline__ bool hit(Cursor&, float, float, float bnx, float bny, float bxx, float bxy) const {
         bool h = false;
         int k = 0;
         for (; k + 4 <= K; k += 4) {
@@ -110,27 +114,32 @@ struct CollideSmemAll {
 };
 
 /* uniform-grid culled: only the obstacles registered in the cells the bbox touches.
- * cell(x) = clamp(floor(x*inv)) is monotone, obstacles are registered with the same
- * function, so every obstacle that can overlap the bbox shares a cell with it: the
- * flag is identical to the exhaustive test. */
+ * cell(v) = clamp(floor(v*inv)) is monotone and obstacles are registered with the same
+ * function, so every obstacle that can overlap the bbox shares a cell with it: the flag
+ * is identical to the exhaustive test.  The bbox corners are the step's two end points,
+ * so its cell range is the min/max of their cells (one conversion pair per step, the
+ * other carried in the cursor); the cells of one grid row are contiguous in the CSR. */
 struct CollideGrid {
     const int* cellStart;      /* [C*C+1] */
     const float4* items;       /* obstacle AABBs, grouped by cell */
     int C; float invX, invY;
+    struct Cursor { int cx, cy; };
     __device__ __forceinline__ int cell(float v, float inv) const {
         return min(max(__float2int_rd(__fmul_rn(v, inv)), 0), C - 1);
     }
-    __device__ __forceinline__ bool hit(float bnx, float bny, float bxx, float bxy) const {
-        const int cx0 = cell(bnx, invX), cx1 = cell(bxx, invX), cy0 = cell(bny, invY), cy1 = cell(bxy, invY);
-        for (int cy = cy0; cy <= cy1; ++cy) {
-            for (int cx = cx0; cx <= cx1; ++cx) {
-                const int c = cy * C + cx;
-                const int e = cellStart[c + 1];
-                for (int k = cellStart[c]; k < e; ++k)
-                    if (aabb_overlap(bnx, bny, bxx, bxy, items[k])) return true;
-            }
+    __device__ __forceinline__ Cursor start(float x, float y) const { return Cursor{cell(x, invX), cell(y, invY)}; }
+    __device__ __forceinline__ bool hit(Cursor& cur, float x, float y, float bnx, float bny, float bxx, float bxy) const {
+        const int cxn = cell(x, invX), cyn = cell(y, invY);
+        const int cx0 = min(cur.cx, cxn), cx1 = max(cur.cx, cxn);
+        const int cy0 = min(cur.cy, cyn), cy1 = max(cur.cy, cyn);
+        cur.cx = cxn; cur.cy = cyn;
+        bool h = false;
+        for (int cy = cy0; cy <= cy1 && !h; ++cy) {
+            const int row = cy * C;
+            const int e = cellStart[row + cx1 + 1];
+            for (int k = cellStart[row + cx0]; k < e && !h; ++k) h = aabb_overlap(bnx, bny, bxx, bxy, items[k]);
         }
-        return false;
+        return h;
     }
 };
 
@@ -140,27 +149,29 @@ struct CollideGrid {
  * bounds (:42-45, theta/v NOT advanced when it fires), then theta/v, then the
  * step bbox (:49-59) against the obstacles (:61-64).  The state at the moment of
  * exit is returned whether or not the edge is valid (:67-73).  tanf(steering) is
- * loop-invariant (the reference recomputes it every step, :36). */
+ * loop-invariant (the reference recomputes it every step, :36); v / L is exact for L = 1. */
 struct DynParams { float W, H, L; int numDisc; };
 
 template <class Collide>
 __device__ __forceinline__ bool propagate_edge(float4& s, const Controls& u, const DynParams& p, const Collide& col) {
     const float dt = __fdiv_rn(u.duration, (float)p.numDisc);
     const float tanS = tanf(u.steering);
+    const bool unitL = (p.L == 1.0f);
     float x = s.x, y = s.y, th = s.z, v = s.w;
+    typename Collide::Cursor cur = col.start(x, y);
     bool valid = true;
     for (int i = 0; i < p.numDisc; ++i) {
         const float px = x, py = y;
-        float sn, cs;
-        sn = sinf(th); cs = cosf(th);
+        const float sn = sinf(th), cs = cosf(th);
         x = __fmaf_rn(dt, __fmul_rn(v, cs), x);
         y = __fmaf_rn(dt, __fmul_rn(v, sn), y);
         if (x <= 0.0f || x >= p.W || y <= 0.0f || y >= p.H) { valid = false; break; }
-        th = __fmaf_rn(dt, __fmul_rn(__fdiv_rn(v, p.L), tanS), th);
+        const float vl = unitL ? v : __fdiv_rn(v, p.L);
+        th = __fmaf_rn(dt, __fmul_rn(vl, tanS), th);
         v = __fmaf_rn(u.a, dt, v);
         const float bnx = (px > x) ? x : px, bxx = (px > x) ? px : x;
         const float bny = (py > y) ? y : py, bxy = (py > y) ? py : y;
-        if (col.hit(bnx, bny, bxx, bxy)) { valid = false; break; }
+        if (col.hit(cur, x, y, bnx, bny, bxx, bxy)) { valid = false; break; }
     }
     s = make_float4(x, y, th, v);
     return valid;

@@ -1,23 +1,27 @@
 /* kgmt_kernels.cuh — the sm_100a kernels of the KGMT tree-expansion step.
  *
- * One fused kernel per iteration replaces the reference's
+ * One persistent cooperative kernel replaces the reference's per-iteration
  *   scan(R1Avail)+updateR1, scan(G)+findInd, propagateG|propagateGV2,
  *   scan(GNew)+findInd, updateG      (src/planners/KGMT.cu:118-259)
- * and, launched cooperatively, the whole host loop of KGMT::plan.
+ * and the whole host loop of KGMT::plan around them.
  *
  *   stage 1  frontier  = the contiguous node range appended by the previous
  *            iteration (no scan: KGMT.cu:378,451,568,582 make G exactly that);
  *            R1 scores are produced by the CTA that finishes an iteration last.
- *   stage 2  stateless Philox4x32-10 per candidate slot (kgmt_device.cuh).
- *   stage 3  Euler car dynamics on SoA float4 node storage.
- *   stage 4  step-bbox vs obstacle AABBs staged in shared memory by bulk
- *            async copies (cp.async.bulk + mbarrier): exhaustive, or culled
- *            through a uniform grid (identical flags).
- *   stage 5  region counters (R1 family in per-CTA shared-memory histograms,
- *            R2 family with global reductions), accept test on the
- *            iteration-start snapshot, ordered insertion through a single-pass
- *            decoupled look-back scan over candidate tiles (ballot/popc inside
- *            the tile) — accepted nodes go straight from registers to the tree.
+ *   phase A  (warps fully independent, no CTA barrier) per 32-candidate chunk:
+ *     stage 2  stateless Philox4x32-10 per candidate slot (kgmt_device.cuh)
+ *     stage 3  Euler car dynamics on SoA float4 node storage
+ *     stage 4  step-bbox vs obstacle AABBs staged in shared memory by bulk async
+ *              copies (cp.async.bulk + mbarrier): exhaustive, or culled through a
+ *              uniform grid (identical flags)
+ *     stage 5a region counters (R1 family in per-CTA shared-memory histograms, R2
+ *              family with global reductions), accept test on the iteration-start
+ *              snapshot; accepted candidates are ballot-compacted inside the chunk
+ *              into a staging row, the ballot mask is the chunk's scan input
+ *   grid barrier
+ *   phase B  stage 5b ordered insertion: block sums + a 256-wide scan of the chunk
+ *            popcounts give every accepted candidate its tree slot in candidate
+ *            order; rows move staging -> tree with float4 loads/stores; goal test.
  *
  * Canonical semantics where the reference races: SURVEY.md Appendix B.
  */
@@ -31,8 +35,11 @@
 namespace kgmt {
 namespace cg = cooperative_groups;
 
-constexpr int TILE = 256;                 /* candidates per tile == threads per CTA */
+constexpr int TILE = 256;                 /* threads per CTA */
 constexpr int WARPS = TILE / 32;
+constexpr int CHUNK = 32;                 /* candidates per chunk == one warp */
+constexpr int BLK_CHUNKS = 256;           /* chunks per scan block (one per thread of a CTA in phase B) */
+constexpr int SMALL_M = 256;              /* iterations this small run on CTA 0 alone (one grid barrier instead of two) */
 
 enum { STOP_RUNNING = 0, STOP_SOLVED = 1, STOP_TREE_FULL = 2, STOP_ITER_LIMIT = 3, STOP_FRONTIER_EMPTY = 4 };
 enum { COL_GRID_SMEM = 0, COL_GRID_GLOBAL = 1, COL_BRUTE_SMEM = 2, COL_BRUTE_GLOBAL = 3 };
@@ -42,8 +49,8 @@ enum { FLAG_VALID = 1, FLAG_ACCEPT = 2 };
 struct DevState {
     int treeSize, frontierStart, frontierCount, itr;           /* itr = iteration about to run (1-based) */
     int stop, goalIdx; float costToGoal; float R1Threshold;
-    int mode, children, M, numTiles;                            /* shape of the iteration about to run */
-    unsigned ticket, ctasDone; unsigned epoch; int forceChildren;
+    int mode, children, M, numChunks;                           /* shape of the iteration about to run */
+    unsigned ticket, ctasDone; int scoreSel; int forceChildren;   /* scoreSel: which R1Score buffer this iteration reads */
     unsigned long long goalBest;                                /* (cost bits << 32) | tree index, ~0 = none */
     long long expansions;
     int lastMode, lastChildren, lastFrontier, lastM, lastAccepted, lastItr, iterationsDone, pad;
@@ -55,18 +62,21 @@ struct KArgs {
     float4* treeCtrl;             /* (a, steering, duration, cost) */
     int*    treeParent;
     /* occupancy maps */
-    int *R1, *R1Valid, *R1Invalid, *R1Avail, *R1Cov; float* R1Score;
+    int *R1, *R1Valid, *R1Invalid, *R1Avail, *R1Cov; float* R1Score[2];   /* scores: double-buffered (current / next) */
     int *R2, *R2Valid, *R2Invalid; unsigned* R2Stamp;
     /* per-candidate records (null unless recording) */
     float4* candState; float4* candCtrl; int* candParent; int* candR1; int* candR2; unsigned char* candFlags;
-    /* scan */
-    unsigned long long* tileStatus;
+    /* ordered insertion */
+    unsigned* chunkMask;          /* [chunks] accept ballot of each 32-candidate chunk */
+    int* blockSum;                /* [chunks / 256 + 1] accepted candidates per scan block; zero between iterations */
+    float4* stageState; float4* stageCtrl;   /* [maxCand] accepted rows, compacted inside their chunk */
     DevState* st;
     /* collision */
     const float4* obstacles; int K;
     const int* cellStart; const float4* cellItems; int cullC; float cullInvX, cullInvY; int cellStartInts; int numItems;
     int obsTile;                  /* obstacles per shared-memory tile (stream mode) */
-    unsigned long long* iterLog;  /* [256][2]: (globaltimer ns, M<<32 | accepted) per finished iteration; null = off */
+    unsigned long long* iterLog;  /* [256][8]: per finished iteration {end ns, M<<32|accepted, CTA0: start, phase A done,
+                                     barrier 1 passed, phase B done, barrier 2 passed, -}; null = off */
     /* parameters */
     float W, H, L, R1Size, R2Size, goalX, goalY, goalR;
     int N, n, c1, numDisc, maxTree, numIterations, useHist;
@@ -120,7 +130,7 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
  * n*n flags (:510-514) — the same integer.  The sum order is fixed (the reference's
  * cub::BlockReduce order is unspecified): p[t] = sum_k score[t+1024k], then a
  * stride-halving tree (DESIGN.md "scores"; the CPU checker restates the same order). */
-__device__ void scores_block(const KArgs& A, float* p /* smem [1024] */) {
+__device__ void scores_block(const KArgs& A, float* p /* smem [1024] */, float* out /* [c1] */) {
     const int tid = threadIdx.x, c1 = A.c1;
     const float nn = (float)(A.n * A.n);
     int availLocal = 0;
@@ -140,7 +150,7 @@ __device__ void scores_block(const KArgs& A, float* p /* smem [1024] */) {
                 const double den = __dmul_rn((double)__fadd_rn(1.0f, covR), __dadd_rn(1.0, __dmul_rn(r, r)));
                 score = __double2float_rn(__ddiv_rn(f4, den));
             }
-            A.R1Score[c] = score;                       /* raw; normalised below */
+            out[c] = score;                             /* raw; normalised below */
             acc = __fadd_rn(acc, score);
         }
         p[t] = acc;
@@ -157,7 +167,7 @@ __device__ void scores_block(const KArgs& A, float* p /* smem [1024] */) {
     const float total = p[0];
     if (tid == 0) A.st->R1Threshold = sAvail ? __fdiv_rn(total, (float)sAvail) : 0.0f;
     for (int c = tid; c < c1; c += TILE)
-        A.R1Score[c] = (__ldcg(&A.R1Avail[c]) == 0) ? 1.0f : __fdiv_rn(A.R1Score[c], total);
+        out[c] = (__ldcg(&A.R1Avail[c]) == 0) ? 1.0f : __fdiv_rn(out[c], total);
     __syncthreads();
 }
 
@@ -173,22 +183,38 @@ __device__ __forceinline__ void expansion_shape(int active, int treeSize, int ma
     } else { mode = 1; children = 32; M = 32 * active; }
 }
 
-/* end of an iteration: executed by every thread of the CTA that finished last.
+/* sum of v over the CTA (all TILE threads call; result in every thread) */
+__device__ __forceinline__ int block_sum(int v, int* sRed /* [WARPS] */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sRed[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) t += sRed[w];
+    return t;
+}
+
+/* end of an iteration: executed by every thread of ONE CTA after all insertions are visible.
  * KGMT.cu:249-259 + the next iteration's :119-136. */
-__device__ void finalize_iteration(const KArgs& A, float* p) {
+__device__ void finalize_iteration(const KArgs& A, float* p, int* sRed, bool withScores) {
     volatile DevState* st = A.st;
-    __shared__ int sRun;
+    __shared__ int sRun, sSel;
+    const int numBlocks = (st->numChunks + BLK_CHUNKS - 1) / BLK_CHUNKS;
+    int mine = 0;
+    for (int b = threadIdx.x; b < numBlocks; b += TILE) { mine += __ldcg(&A.blockSum[b]); A.blockSum[b] = 0; }
+    const int accepted = block_sum(mine, sRed);
     if (threadIdx.x == 0) {
-        const int M = st->M, numTiles = st->numTiles;
-        const int accepted = (int)(unsigned)ld_relaxed_u64(&A.tileStatus[numTiles - 1]);   /* inclusive total */
-        st->lastMode = st->mode; st->lastChildren = st->children; st->lastFrontier = st->frontierCount;
-        st->lastM = M; st->lastAccepted = accepted; st->lastItr = st->itr;
+        const int M = st->M;
         if (A.iterLog && st->iterationsDone < 255) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            A.iterLog[2 * st->iterationsDone] = t;
-            A.iterLog[2 * st->iterationsDone + 1] = ((unsigned long long)(unsigned)M << 32) | (unsigned)accepted;
+            A.iterLog[8 * st->iterationsDone] = t;
+            A.iterLog[8 * st->iterationsDone + 1] = ((unsigned long long)(unsigned)M << 32) | (unsigned)accepted;
         }
+        st->lastMode = st->mode; st->lastChildren = st->children; st->lastFrontier = st->frontierCount;
+        st->lastM = M; st->lastAccepted = accepted; st->lastItr = st->itr;
         st->iterationsDone += 1;
         st->expansions += M;
         st->frontierStart = st->treeSize;
@@ -207,28 +233,150 @@ __device__ void finalize_iteration(const KArgs& A, float* p) {
             int mode, children, Mn;
             const int ts = st->treeSize, fc = st->forceChildren;
             expansion_shape(accepted, ts, A.maxTree, fc, mode, children, Mn);
-            st->mode = mode; st->children = children; st->M = Mn; st->numTiles = (Mn + TILE - 1) / TILE;
+            st->mode = mode; st->children = children; st->M = Mn; st->numChunks = (Mn + CHUNK - 1) / CHUNK;
         }
-        st->epoch += 1;
         st->ticket = 0; st->ctasDone = 0;
         sRun = (stop == STOP_RUNNING);
+        sSel = st->scoreSel;
+        if (sRun) st->scoreSel = sSel ^ 1;             /* the next iteration reads the scores of the maps as they are now */
     }
     __syncthreads();
-    if (sRun) scores_block(A, p);
+    if (withScores && sRun) scores_block(A, p, A.R1Score[sSel ^ 1]);
     __threadfence();
 }
 
-/* ------------------------------------------------------------------ stages 2-5 fused -- */
-template <int COL, bool LOOP, bool RECORD>
-__global__ void __launch_bounds__(TILE) expand_kernel(const KArgs A) {
+/* per-iteration scalars, read once by every thread */
+struct IterView { int itr, treeSize, frontierStart, children, M, numChunks; uint32_t key0; const float* score; float* scoreNext; };
+
+/* ---------------------------------------------------------------- phase A: one chunk ---
+ * 32 candidates, one per lane: stages 2-5a.  No communication outside the warp. */
+template <class Collide, bool RECORD>
+__device__ __forceinline__ void expand_chunk(const KArgs& A, const IterView& it, const DynParams& dyn,
+                                             const Collide& col, int c, int lane, int* hV, int* hI) {
+    const int s = c * CHUNK + lane;
+    const bool live = s < it.M;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    Controls u{0.f, 0.f, 0.f, 0.f};
+    int parent = -1, r1 = -1, r2 = -1;
+    bool valid = false, accept = false;
+    float parentCost = 0.f;
+    if (live) {
+        parent = it.frontierStart + s / it.children;                       /* KGMT.cu:374-376 / :454 */
+        x = __ldcg(&A.treeState[parent]);                                  /* L2-coherent: written by other SMs last iteration */
+        parentCost = __ldcg(&A.treeCtrl[parent]).w;
+        u = sample_controls((uint32_t)s, it.key0);
+        valid = propagate_edge(x, u, dyn, col);
+        r1 = region_r1(x.x, x.y, A.R1Size, A.N);                           /* KGMT.cu:390 */
+        r2 = region_r2(x.x, x.y, r1, A.R1Size, A.N, A.R2Size, A.n);        /* KGMT.cu:391 */
+        /* maps + accept, KGMT.cu:392-411 on the iteration-start snapshot (App. B #1,#2) */
+        if (r1 >= 0) {
+            if (valid) {
+                accept = u.u3 <= __ldcg(&it.score[r1]);
+                if (r2 >= 0) {
+                    const unsigned stamp = __ldcg(&A.R2Stamp[r2]);
+                    if (stamp == 0u || stamp > (unsigned)it.itr) accept = true;    /* unavailable at iteration start */
+                    if (stamp == 0u) {
+                        if (atomicCAS(&A.R2Stamp[r2], 0u, (unsigned)it.itr + 1u) == 0u) atomicAdd(&A.R1Cov[r1], 1);
+                    }
+                    atomicAdd(&A.R2Valid[r2], 1);
+                }
+            } else if (r2 >= 0) {
+                atomicAdd(&A.R2Invalid[r2], 1);
+            }
+            if (r2 >= 0) atomicAdd(&A.R2[r2], 1);
+            if (A.useHist) {
+                atomicAdd(valid ? &hV[r1] : &hI[r1], 1);
+            } else {
+                atomicAdd(&A.R1[r1], 1);
+                if (valid) { atomicAdd(&A.R1Valid[r1], 1); A.R1Avail[r1] = 1; }
+                else atomicAdd(&A.R1Invalid[r1], 1);
+            }
+        }
+    }
+    /* ballot compaction inside the chunk; the mask is the input of the ordered scan (phase B) */
+    const unsigned bal = __ballot_sync(0xffffffffu, accept);
+    if (accept) {
+        const int at = c * CHUNK + __popc(bal & ((1u << lane) - 1u));
+        __stcg(&A.stageState[at], x);
+        __stcg(&A.stageCtrl[at], make_float4(u.a, u.steering, u.duration, __fadd_rn(parentCost, u.duration)));  /* :585-586 */
+    }
+    if (lane == 0) {
+        __stcg(&A.chunkMask[c], bal);
+        if (bal) atomicAdd(&A.blockSum[c / BLK_CHUNKS], __popc(bal));
+    }
+    if (RECORD && live) {
+        A.candState[s] = x;
+        A.candCtrl[s] = make_float4(u.a, u.steering, u.duration, u.u3);
+        A.candParent[s] = parent;
+        A.candR1[s] = r1; A.candR2[s] = r2;
+        A.candFlags[s] = (unsigned char)((valid ? FLAG_VALID : 0) | (accept ? FLAG_ACCEPT : 0));
+    }
+}
+
+/* -------------------------------------------------------- phase B: one scan block ------
+ * updateG (KGMT.cu:555-591) for the accepted candidates of 256 consecutive chunks.  Thread t
+ * loads the ballot of chunk blk*256+t; a CTA-wide scan of the popcounts orders the rows; each
+ * warp then moves the rows of its 32 chunks with all lanes busy: row q of the warp belongs to
+ * the chunk found by a 5-step shuffle search over the inclusive counts.
+ * base = accepted candidates in all earlier blocks. */
+__device__ __forceinline__ void insert_block(const KArgs& A, const IterView& it, int blk, int base, int* sScan /* [WARPS] */) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blk * BLK_CHUNKS + tid;
+    const unsigned mask = (c < it.numChunks) ? __ldcg(&A.chunkMask[c]) : 0u;
+    const int cnt = __popc(mask);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    __syncthreads();
+    if (lane == 31) sScan[warp] = incl;
+    __syncthreads();
+    int warpBase = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) if (w < warp) warpBase += sScan[w];
+    const int W = __shfl_sync(0xffffffffu, incl, 31);          /* rows of this warp's 32 chunks */
+    const int c0 = blk * BLK_CHUNKS + warp * 32;
+    const int dst0 = it.treeSize + base + warpBase;
+    for (int q0 = 0; q0 < W; q0 += 32) {
+        const int q = q0 + lane;
+        int i = 0;                                             /* number of chunks whose inclusive count <= q */
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int v = __shfl_sync(0xffffffffu, incl, i + step - 1);
+            if (v <= q) i += step;
+        }
+        i = min(i, 31);
+        const unsigned m = __shfl_sync(0xffffffffu, mask, i);
+        const int excl = __shfl_sync(0xffffffffu, incl - cnt, i);
+        if (q < W) {
+            const int r = q - excl;
+            const int bit = (int)__fns(m, 0, r + 1);
+            const int ci = c0 + i;
+            const float4 x = __ldcg(&A.stageState[ci * CHUNK + r]);
+            const float4 u = __ldcg(&A.stageCtrl[ci * CHUNK + r]);
+            const int dst = dst0 + q;
+            A.treeState[dst] = x;
+            A.treeCtrl[dst] = u;
+            A.treeParent[dst] = it.frontierStart + (ci * CHUNK + bit) / it.children;
+            if (in_goal(x.x, x.y, A.goalX, A.goalY, A.goalR))              /* :589; canonical min (App. B #5) */
+                atomicMin(&A.st->goalBest, ((unsigned long long)__float_as_uint(u.w) << 32) | (unsigned)dst);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ the planner kernel --
+ * Cooperative launch, grid = resident CTAs.  Runs up to maxIters expansion iterations
+ * (1 = kgmt_expand_iteration, numIterations = kgmt_plan) or until the planner stops. */
+template <int COL, bool RECORD>
+__global__ void __launch_bounds__(TILE) expand_kernel(const KArgs A, int maxIters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t sBar;
-    __shared__ int sWarpCount[WARPS];
-    __shared__ int sTile, sBase, sLast;
+    __shared__ int sRed[WARPS];
+    __shared__ int sLast;
     __shared__ float sP[1024];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     DevState* st = A.st;
+    cg::grid_group grid = cg::this_grid();
 
     /* shared-memory carve-up: [R1 histograms][collision data] */
     int* hV = reinterpret_cast<int*>(smem_raw);
@@ -260,161 +408,111 @@ __global__ void __launch_bounds__(TILE) expand_kernel(const KArgs A) {
             sObs = reinterpret_cast<const float4*>(colBase);
         }
     }
-
     const DynParams dyn{A.W, A.H, A.L, A.numDisc};
+    const CollideGrid colGridS{sCellStart, sItems, A.cullC, A.cullInvX, A.cullInvY};
+    const CollideGrid colGridG{A.cellStart, A.cellItems, A.cullC, A.cullInvX, A.cullInvY};
+    const CollideSmemAll colAllS{sObs, A.K};
+    const CollideSmemAll colAllG{A.obstacles, A.K};
 
-    for (;;) {
-        /* iteration scalars (written by the previous finalize, ordered by the launch boundary or grid.sync) */
-        const int stop = *(volatile int*)&st->stop;
-        if (stop != STOP_RUNNING) break;
-        const int itr = *(volatile int*)&st->itr;
-        const int treeSize = *(volatile int*)&st->treeSize;
-        const int frontierStart = *(volatile int*)&st->frontierStart;
-        const int children = *(volatile int*)&st->children;
-        const int M = *(volatile int*)&st->M;
-        const int numTiles = *(volatile int*)&st->numTiles;
-        const unsigned epoch = *(volatile unsigned*)&st->epoch;
-        const uint32_t key0 = A.seed + (uint32_t)itr;
-        const unsigned stampNew = (unsigned)itr + 1u;          /* R2 cells first reached in this iteration */
+    auto run_chunk = [&](const IterView& it, int c) {
+        if (COL == COL_GRID_SMEM)        expand_chunk<CollideGrid, RECORD>(A, it, dyn, colGridS, c, lane, hV, hI);
+        else if (COL == COL_GRID_GLOBAL) expand_chunk<CollideGrid, RECORD>(A, it, dyn, colGridG, c, lane, hV, hI);
+        else if (COL == COL_BRUTE_SMEM)  expand_chunk<CollideSmemAll, RECORD>(A, it, dyn, colAllS, c, lane, hV, hI);
+        else                             expand_chunk<CollideSmemAll, RECORD>(A, it, dyn, colAllG, c, lane, hV, hI);
+    };
+    auto flush_hist = [&]() {          /* R1 = R1Valid + R1Invalid increments, KGMT.cu:392,406,409 */
+        if (!A.useHist) return;
+        for (int c = tid; c < A.c1; c += TILE) {
+            const int v = hV[c], iv = hI[c];
+            if (v | iv) {
+                atomicAdd(&A.R1[c], v + iv);
+                if (v) { atomicAdd(&A.R1Valid[c], v); A.R1Avail[c] = 1; }
+                if (iv) atomicAdd(&A.R1Invalid[c], iv);
+            }
+        }
+    };
 
-        if (A.useHist) {
-            for (int c = tid; c < 2 * A.c1; c += TILE) hV[c] = 0;
+    for (int iter = 0; iter < maxIters; ++iter) {
+        /* iteration scalars (written by the previous finalize, ordered by the launch boundary or the grid barrier) */
+        if (*(volatile int*)&st->stop != STOP_RUNNING) break;
+        IterView it;
+        it.itr = *(volatile int*)&st->itr;
+        it.treeSize = *(volatile int*)&st->treeSize;
+        it.frontierStart = *(volatile int*)&st->frontierStart;
+        it.children = *(volatile int*)&st->children;
+        it.M = *(volatile int*)&st->M;
+        it.numChunks = *(volatile int*)&st->numChunks;
+        it.key0 = A.seed + (uint32_t)it.itr;
+        { const int sel = *(volatile int*)&st->scoreSel; it.score = A.R1Score[sel]; it.scoreNext = A.R1Score[sel ^ 1]; }
+        const int logRow = *(volatile int*)&st->iterationsDone;
+        auto stamp = [&](int col) {
+            if (A.iterLog && blockIdx.x == 0 && tid == 0 && logRow < 255) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                A.iterLog[8 * logRow + col] = t;
+            }
+        };
+        stamp(2);
+
+        if (it.M <= SMALL_M) {
+            /* latency path: the whole iteration on CTA 0, one chunk per warp, CTA barriers only */
+            if (blockIdx.x == 0) {
+                if (A.useHist) for (int c = tid; c < 2 * A.c1; c += TILE) hV[c] = 0;
+                __syncthreads();
+                if (warp < it.numChunks) run_chunk(it, warp);
+                __syncthreads();
+                stamp(3);
+                flush_hist();
+                insert_block(A, it, 0, 0, sRed);
+                __threadfence();
+                __syncthreads();
+                stamp(5);
+                finalize_iteration(A, sP, sRed, true);
+            }
+            grid.sync();
+            stamp(6);
+            continue;
+        }
+
+        /* ---- phase A: chunks handed out by ticket, next ticket prefetched behind the current chunk */
+        if (A.useHist) for (int c = tid; c < 2 * A.c1; c += TILE) hV[c] = 0;
+        __syncthreads();
+        {
+            int t = 0;
+            if (lane == 0) t = (int)atomicAdd(&st->ticket, 1u);
+            int c = __shfl_sync(0xffffffffu, t, 0);
+            while (c < it.numChunks) {
+                if (lane == 0) t = (int)atomicAdd(&st->ticket, 1u);
+                run_chunk(it, c);
+                c = __shfl_sync(0xffffffffu, t, 0);
+            }
         }
         __syncthreads();
+        flush_hist();
+        stamp(3);
+        grid.sync();
+        stamp(4);
 
-        for (;;) {
-            if (tid == 0) sTile = (int)atomicAdd(&st->ticket, 1u);
-            __syncthreads();
-            const int tile = sTile;
-            if (tile >= numTiles) break;
-            const int s = tile * TILE + tid;
-            const bool live = s < M;
+        /* ---- the next iteration's R1 scores (maps are final now) on the CTA least likely to own a scan block,
+         *      overlapped with phase B.  If the planner stops in this iteration they are simply not used. */
+        if (blockIdx.x == gridDim.x - 1) scores_block(A, sP, it.scoreNext);
 
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            Controls u{0.f, 0.f, 0.f, 0.f};
-            int parent = -1, r1 = -1, r2 = -1;
-            bool valid = false, accept = false;
-            float parentCost = 0.f;
-            if (live) {
-                parent = frontierStart + s / children;                             /* KGMT.cu:374-376 / :454 */
-                x = __ldcg(&A.treeState[parent]);              /* L2-coherent: written by other SMs last iteration */
-                parentCost = __ldcg(&A.treeCtrl[parent]).w;
-                u = sample_controls((uint32_t)s, key0);
-                if (COL == COL_GRID_SMEM) {
-                    const CollideGrid col{sCellStart, sItems, A.cullC, A.cullInvX, A.cullInvY};
-                    valid = propagate_edge(x, u, dyn, col);
-                } else if (COL == COL_GRID_GLOBAL) {
-                    const CollideGrid col{A.cellStart, A.cellItems, A.cullC, A.cullInvX, A.cullInvY};
-                    valid = propagate_edge(x, u, dyn, col);
-                } else if (COL == COL_BRUTE_SMEM) {
-                    const CollideSmemAll col{sObs, A.K};
-                    valid = propagate_edge(x, u, dyn, col);
-                } else {
-                    const CollideSmemAll col{A.obstacles, A.K};                   /* global/L1 path */
-                    valid = propagate_edge(x, u, dyn, col);
-                }
-                r1 = region_r1(x.x, x.y, A.R1Size, A.N);                           /* KGMT.cu:390 */
-                r2 = region_r2(x.x, x.y, r1, A.R1Size, A.N, A.R2Size, A.n);        /* KGMT.cu:391 */
-                /* maps + accept, KGMT.cu:392-411 on the iteration-start snapshot (App. B #1,#2) */
-                if (r1 >= 0) {
-                    if (valid) {
-                        accept = u.u3 <= __ldcg(&A.R1Score[r1]);
-                        if (r2 >= 0) {
-                            const unsigned stamp = __ldcg(&A.R2Stamp[r2]);
-                            if (stamp == 0u || stamp > (unsigned)itr) accept = true;       /* unavailable at iteration start */
-                            if (stamp == 0u) {
-                                if (atomicCAS(&A.R2Stamp[r2], 0u, stampNew) == 0u) atomicAdd(&A.R1Cov[r1], 1);
-                            }
-                            atomicAdd(&A.R2Valid[r2], 1);
-                        }
-                    } else if (r2 >= 0) {
-                        atomicAdd(&A.R2Invalid[r2], 1);
-                    }
-                    if (r2 >= 0) atomicAdd(&A.R2[r2], 1);
-                    if (A.useHist) {
-                        atomicAdd(valid ? &hV[r1] : &hI[r1], 1);
-                    } else {
-                        atomicAdd(&A.R1[r1], 1);
-                        if (valid) { atomicAdd(&A.R1Valid[r1], 1); A.R1Avail[r1] = 1; }
-                        else atomicAdd(&A.R1Invalid[r1], 1);
-                    }
-                }
-            }
-
-            /* ordered compaction of accepted candidates: ballot/popc in the warp, look-back across tiles */
-            const unsigned bal = __ballot_sync(0xffffffffu, accept);
-            if (lane == 0) sWarpCount[warp] = __popc(bal);
-            __syncthreads();
-            int warpOff = 0, agg = 0;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) { const int c = sWarpCount[w]; if (w < warp) warpOff += c; agg += c; }
-            if (warp == 0) {
-                int base = 0;
-                const unsigned long long tagA = ((unsigned long long)(epoch * 4u + 1u)) << 32;
-                const unsigned long long tagP = ((unsigned long long)(epoch * 4u + 2u)) << 32;
-                if (tile == 0) {
-                    if (lane == 0) st_relaxed_u64(&A.tileStatus[0], tagP | (unsigned)agg);
-                } else {
-                    if (lane == 0) st_relaxed_u64(&A.tileStatus[tile], tagA | (unsigned)agg);
-                    int j = tile - 1 - lane;
-                    for (;;) {
-                        int flag = 2, val = 0;
-                        if (j >= 0) {
-                            unsigned long long w;
-                            do { w = ld_relaxed_u64(&A.tileStatus[j]); } while ((unsigned)(w >> 34) != epoch);
-                            flag = (int)((w >> 32) & 3u); val = (int)(unsigned)w;
-                        }
-                        const unsigned incl = __ballot_sync(0xffffffffu, flag == 2);
-                        const int first = incl ? (__ffs(incl) - 1) : 32;
-                        int contrib = (lane <= first) ? val : 0;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-                        base += contrib;
-                        if (incl) break;
-                        j -= 32;
-                    }
-                    if (lane == 0) st_relaxed_u64(&A.tileStatus[tile], tagP | (unsigned)(base + agg));
-                }
-                if (lane == 0) sBase = base;
-            }
-            __syncthreads();
-
-            if (accept) {                                                          /* updateG, KGMT.cu:555-591 */
-                const int dst = treeSize + sBase + warpOff + __popc(bal & ((1u << lane) - 1u));
-                const float cost = __fadd_rn(parentCost, u.duration);              /* :585-586, :631-633 */
-                A.treeState[dst] = x;
-                A.treeCtrl[dst] = make_float4(u.a, u.steering, u.duration, cost);
-                A.treeParent[dst] = parent;
-                if (in_goal(x.x, x.y, A.goalX, A.goalY, A.goalR))                  /* :589; canonical min (App. B #5) */
-                    atomicMin(&st->goalBest, ((unsigned long long)__float_as_uint(cost) << 32) | (unsigned)dst);
-            }
-            if (RECORD && live) {
-                A.candState[s] = x;
-                A.candCtrl[s] = make_float4(u.a, u.steering, u.duration, u.u3);
-                A.candParent[s] = parent;
-                A.candR1[s] = r1; A.candR2[s] = r2;
-                A.candFlags[s] = (unsigned char)((valid ? FLAG_VALID : 0) | (accept ? FLAG_ACCEPT : 0));
-            }
-        }
-
-        /* flush the R1-family histograms (R1 = R1Valid + R1Invalid increments, KGMT.cu:392,406,409) */
-        if (A.useHist) {
-            for (int c = tid; c < A.c1; c += TILE) {
-                const int v = hV[c], iv = hI[c];
-                if (v | iv) {
-                    atomicAdd(&A.R1[c], v + iv);
-                    if (v) { atomicAdd(&A.R1Valid[c], v); A.R1Avail[c] = 1; }
-                    if (iv) atomicAdd(&A.R1Invalid[c], iv);
-                }
-            }
+        /* ---- phase B: ordered insertion, scan blocks strided over the CTAs */
+        const int numBlocks = (it.numChunks + BLK_CHUNKS - 1) / BLK_CHUNKS;
+        for (int blk = blockIdx.x; blk < numBlocks; blk += gridDim.x) {
+            int mine = 0;
+            for (int b = tid; b < blk; b += TILE) mine += __ldcg(&A.blockSum[b]);
+            const int base = block_sum(mine, sRed);
+            insert_block(A, it, blk, base, sRed);
         }
         __threadfence();
         __syncthreads();
+        stamp(5);
         if (tid == 0) sLast = (atomicAdd(&st->ctasDone, 1u) == gridDim.x - 1u);
         __syncthreads();
-        if (sLast) { __threadfence(); finalize_iteration(A, sP); }
-        if (!LOOP) break;
-        cg::this_grid().sync();
+        if (sLast) { __threadfence(); finalize_iteration(A, sP, sRed, false); }
+        grid.sync();
+        stamp(6);
     }
 }
 
@@ -496,17 +594,17 @@ __global__ void __launch_bounds__(TILE) begin_kernel(const KArgs A, float4 rootS
         st->goalIdx = -1; st->costToGoal = 0.0f; st->goalBest = ~0ull;
         st->expansions = 0; st->iterationsDone = 0;
         st->lastMode = st->lastChildren = st->lastFrontier = st->lastM = st->lastAccepted = st->lastItr = 0;
-        st->ticket = 0; st->ctasDone = 0; st->epoch += 1;
+        st->ticket = 0; st->ctasDone = 0; st->scoreSel = 0;
         int stop = STOP_RUNNING;
         if (A.numIterations <= 0) stop = STOP_ITER_LIMIT;
         else if (1 >= A.maxTree) stop = STOP_TREE_FULL;
         st->stop = stop;
         int mode = 0, children = 1, M = 0;
         if (stop == STOP_RUNNING) expansion_shape(1, 1, A.maxTree, st->forceChildren, mode, children, M);
-        st->mode = mode; st->children = children; st->M = M; st->numTiles = (M + TILE - 1) / TILE;
+        st->mode = mode; st->children = children; st->M = M; st->numChunks = (M + CHUNK - 1) / CHUNK;
     }
     __syncthreads();
-    scores_block(A, sP);
+    scores_block(A, sP, A.R1Score[0]);
 }
 
 /* kgmt_seed_frontier: `count` nodes already copied into tree[0,count); all are frontier */
@@ -528,17 +626,17 @@ __global__ void __launch_bounds__(TILE) seed_finish_kernel(const KArgs A, int co
         st->goalIdx = -1; st->costToGoal = 0.0f; st->goalBest = ~0ull;
         st->expansions = 0; st->iterationsDone = 0;
         st->lastMode = st->lastChildren = st->lastFrontier = st->lastM = st->lastAccepted = st->lastItr = 0;
-        st->ticket = 0; st->ctasDone = 0; st->epoch += 1;
+        st->ticket = 0; st->ctasDone = 0; st->scoreSel = 0;
         int stop = STOP_RUNNING;
         if (A.numIterations <= 0) stop = STOP_ITER_LIMIT;
         else if (count >= A.maxTree) stop = STOP_TREE_FULL;
         st->stop = stop;
         int mode = 0, children = 1, M = 0;
         if (stop == STOP_RUNNING) expansion_shape(count, count, A.maxTree, st->forceChildren, mode, children, M);
-        st->mode = mode; st->children = children; st->M = M; st->numTiles = (M + TILE - 1) / TILE;
+        st->mode = mode; st->children = children; st->M = M; st->numChunks = (M + CHUNK - 1) / CHUNK;
     }
     __syncthreads();
-    scores_block(A, sP);
+    scores_block(A, sP, A.R1Score[0]);
 }
 
 /* R1Cov[c] = number of available R2 cells of R1 cell c (after import / seeding) */
@@ -557,7 +655,7 @@ __global__ void recount_cov_kernel(const KArgs A) {
 
 __global__ void __launch_bounds__(TILE) scores_kernel(const KArgs A) {
     __shared__ float sP[1024];
-    scores_block(A, sP);
+    scores_block(A, sP, A.R1Score[A.st->scoreSel]);
 }
 
 /* views in the reference's element layout (export) */

@@ -294,11 +294,10 @@ class KGMT:
         return dict(zip(keys, list(out)))
 
     def iteration_log(self, enable=True):
-        """Rows (t_ns since the first row, candidates, accepted) of the last plan; call once with enable to switch on."""
-        buf = (C.c_ulonglong * (3 * 256))()
+        """Rows of 8 u64 (see kgmt_iteration_log) of the last plan; call once with enable to switch logging on."""
+        buf = (C.c_ulonglong * (8 * 256))()
         n = self._ck(load().kgmt_iteration_log(self._h, int(enable), buf, 256))
-        a = np.array(list(buf), dtype=np.uint64).reshape(-1, 3)[:n]
-        return a
+        return np.array(list(buf), dtype=np.uint64).reshape(-1, 8)[:n]
 
     @property
     def launch_count(self):

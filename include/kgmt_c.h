@@ -181,9 +181,10 @@ float kgmt_r1_size(const kgmt_ctx* ctx);                         /* KGMT::R1Size
 float kgmt_r2_size(const kgmt_ctx* ctx);                         /* KGMT::R2Size_, KGMT.cu:14 */
 void* kgmt_stream(const kgmt_ctx* ctx);                          /* cudaStream_t the context launches on */
 long long kgmt_launch_count(const kgmt_ctx* ctx);                /* kernels of this library launched so far */
-/* diagnostics: enable != 0 turns on per-iteration device timestamps; out3 rows = {globaltimer ns at the end of
- * the iteration, candidates, accepted} of the last plan; returns rows written */
-int  kgmt_iteration_log(kgmt_ctx* ctx, int enable, unsigned long long* out3, int max_rows);
+/* diagnostics: enable != 0 turns on per-iteration device timestamps; out8 rows (8 x u64) = {globaltimer ns when the
+ * iteration was finalized, candidates << 32 | accepted, then CTA 0's globaltimer at: iteration start, phase A done,
+ * first grid barrier passed, phase B done, last grid barrier passed, 0} of the last plan; returns rows written */
+int  kgmt_iteration_log(kgmt_ctx* ctx, int enable, unsigned long long* out8, int max_rows);
 /* out8 = {collision back end (0 grid/smem, 1 grid/L1, 2 exhaustive/smem, 3 exhaustive/L1), cull cells per side,
  *         cull grid items, dynamic shared memory bytes, persistent grid size, SM count, R1 smem histograms, K} */
 int  kgmt_get_config(const kgmt_ctx* ctx, int* out8);

@@ -18,7 +18,12 @@ log = p.iteration_log()
 print("plan", r, "ms", ms)
 t = log[:, 0].astype(np.int64); dt = np.diff(t, prepend=t[0])
 for i, row in enumerate(log):
-    print("itr %2d  M %8d acc %7d  dt %8.1f us" % (i + 1, row[1], row[2], dt[i] / 1e3))
+    r = row.astype(np.int64)
+    ph = [(r[k] - r[2]) / 1e3 if r[k] else float("nan") for k in (3, 4, 5, 0, 6)]
+    print("itr %2d  M %8d acc %7d  dt %7.1f us | CTA0: A done %6.1f  bar1 %6.1f  B done %6.1f  finalized %6.1f  bar2 %6.1f" % (
+        i + 1, r[1] >> 32, r[1] & 0xFFFFFFFF, dt[i] / 1e3, *ph))
+if len(sys.argv) > 1 and sys.argv[1] == "timeline":
+    sys.exit(0)
 print("---- sweep")
 for cull in (16, 32, 48, 64, 96, 128):
     for lim in (48 * 1024, 200 * 1024, 1):
