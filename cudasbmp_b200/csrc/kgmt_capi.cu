@@ -475,12 +475,16 @@ static int launch_expand(kgmt_ctx* ctx, int maxIters) {
     return KGMT_OK;
 }
 
-int kgmt_expand_iteration(kgmt_ctx* ctx, kgmt_iter_stats* out) {
-    if (!ctx) return KGMT_ERR_INVALID;
-    if (!ctx->begun) return fail(ctx, KGMT_ERR_STATE, "kgmt_expand_iteration before kgmt_begin / kgmt_seed_frontier");
+int kgmt_expand_iteration(kgmt_ctx* ctx, kgmt_iter_stats* out) { return kgmt_expand_iterations(ctx, 1, out); }
+
+/* up to `count` while-loop bodies (KGMT.cu:118-259) in ONE cooperative launch; stops early when the planner stops.
+ * `out` describes the last iteration executed. */
+int kgmt_expand_iterations(kgmt_ctx* ctx, int count, kgmt_iter_stats* out) {
+    if (!ctx || count < 1) return KGMT_ERR_INVALID;
+    if (!ctx->begun) return fail(ctx, KGMT_ERR_STATE, "kgmt_expand_iteration(s) before kgmt_begin / kgmt_seed_frontier");
     CU(cudaSetDevice(ctx->device));
     if (ctx->hState->stop == STOP_RUNNING) {
-        int rc = launch_expand(ctx, 1);
+        int rc = launch_expand(ctx, count);
         if (rc) return rc;
         rc = fetch_state(ctx);
         if (rc) return rc;

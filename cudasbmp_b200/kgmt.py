@@ -34,7 +34,7 @@ _DTYPE = {ARR_SAMPLES: (np.float32, 7), ARR_UNEXPLORED: (np.float32, 7), ARR_PAR
 # every symbol include/kgmt_c.h declares
 ABI_SYMBOLS = [
     "kgmt_abi_version", "kgmt_default_params", "kgmt_create", "kgmt_destroy", "kgmt_last_error", "kgmt_reset", "kgmt_set_seed",
-    "kgmt_set_obstacles", "kgmt_set_obstacles_host", "kgmt_plan", "kgmt_begin", "kgmt_expand_iteration",
+    "kgmt_set_obstacles", "kgmt_set_obstacles_host", "kgmt_plan", "kgmt_begin", "kgmt_expand_iteration", "kgmt_expand_iterations",
     "kgmt_get_result", "kgmt_extract_path", "kgmt_stage_scores", "kgmt_stage_propagate", "kgmt_seed_frontier",
     "kgmt_set_children", "kgmt_checkpoint", "kgmt_restore", "kgmt_export", "kgmt_import", "kgmt_array_bytes",
     "kgmt_dump_csv", "kgmt_tree_size", "kgmt_cost_to_goal", "kgmt_r1_size", "kgmt_r2_size", "kgmt_stream",
@@ -100,6 +100,7 @@ def load():
     L.kgmt_plan.argtypes = [vp, f32p, f32p, C.POINTER(Result)]
     L.kgmt_begin.argtypes = [vp, f32p, f32p]
     L.kgmt_expand_iteration.argtypes = [vp, C.POINTER(IterStats)]
+    L.kgmt_expand_iterations.argtypes = [vp, C.c_int, C.POINTER(IterStats)]
     L.kgmt_get_result.argtypes = [vp, C.POINTER(Result)]
     L.kgmt_extract_path.argtypes = [vp, C.c_int, f32p, C.c_int]
     L.kgmt_stage_scores.argtypes = [vp]
@@ -225,6 +226,13 @@ class KGMT:
     def iterate(self):
         s = IterStats()
         self._ck(load().kgmt_expand_iteration(self._h, C.byref(s)))
+        self.treeSize_, self.costToGoal_ = s.tree_size, s.cost_to_goal
+        return s.as_dict()
+
+    def iterate_many(self, count):
+        """Up to `count` iterations in one launch; returns the stats of the last one executed."""
+        s = IterStats()
+        self._ck(load().kgmt_expand_iterations(self._h, int(count), C.byref(s)))
         self.treeSize_, self.costToGoal_ = s.tree_size, s.cost_to_goal
         return s.as_dict()
 

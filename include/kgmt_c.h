@@ -144,6 +144,8 @@ int  kgmt_plan(kgmt_ctx* ctx, const float* initial7, const float* goal7, kgmt_re
 /* the same, split: root insertion (KGMT.cu:85-114) then one while-loop body (KGMT.cu:118-259) per call */
 int  kgmt_begin(kgmt_ctx* ctx, const float* initial7, const float* goal7);
 int  kgmt_expand_iteration(kgmt_ctx* ctx, kgmt_iter_stats* out);
+/* up to `count` loop bodies in one launch (stops early when the planner stops); `out` = the last one executed */
+int  kgmt_expand_iterations(kgmt_ctx* ctx, int count, kgmt_iter_stats* out);
 int  kgmt_get_result(kgmt_ctx* ctx, kgmt_result* out);
 /* back-trace of the parent links from the goal node (or any node) to the root: rows of 7 floats,
  * root first.  Returns the path length (may exceed max_rows; only max_rows are written). */
