@@ -41,7 +41,8 @@ struct kgmt_ctx {
     int *candParent = nullptr, *candR1 = nullptr, *candR2 = nullptr;
     unsigned char* candFlags = nullptr;
     bool recordAllocated = false;
-    unsigned* chunkMask = nullptr; int* blockSum = nullptr; size_t numBlocksCap = 0;
+    unsigned* chunkMask = nullptr; int* blockSum = nullptr; unsigned* ticket = nullptr;
+    size_t chunksCap = 0, blocksCap = 0;
     float4 *stageState = nullptr, *stageCtrl = nullptr;
     unsigned long long* iterLog = nullptr;
     DevState* dState = nullptr;
@@ -120,7 +121,9 @@ static KArgs make_args(const kgmt_ctx* c) {
     A.R2 = c->R2; A.R2Valid = c->R2Valid; A.R2Invalid = c->R2Invalid; A.R2Stamp = c->R2Stamp;
     A.candState = c->candState; A.candCtrl = c->candCtrl; A.candParent = c->candParent;
     A.candR1 = c->candR1; A.candR2 = c->candR2; A.candFlags = c->candFlags;
-    A.chunkMask = c->chunkMask; A.blockSum = c->blockSum; A.stageState = c->stageState; A.stageCtrl = c->stageCtrl;
+    A.chunkMask = c->chunkMask; A.blockSum = c->blockSum; A.ticket = c->ticket;
+    A.stageState = c->stageState; A.stageCtrl = c->stageCtrl;
+    A.chunksCap = (int)c->chunksCap; A.blocksCap = (int)c->blocksCap; A.maxCand = c->maxCand; A.totalWarps = c->gridLoop * WARPS;
     A.st = c->dState;
     A.obstacles = c->dObs; A.K = c->K;
     A.cellStart = c->dCellStart; A.cellItems = c->dCellItems; A.cullC = c->cullC;
@@ -273,7 +276,7 @@ static int clear_state(kgmt_ctx* ctx, bool sync) {
         CU(cudaMemsetAsync(ctx->treeParent, 0xFF, T * 4, ctx->stream));
     }
     CU(cudaMemsetAsync(ctx->mapSlab, 0, ctx->mapSlabInts * 4, ctx->stream));
-    CU(cudaMemsetAsync(ctx->blockSum, 0, ctx->numBlocksCap * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->blockSum, 0, 3 * ctx->blocksCap * 4, ctx->stream));
     fill_float_kernel<<<(2 * ctx->c1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->R1Score[0], 1.0f, (size_t)2 * ctx->c1);
     if (ctx->recordAllocated) {
         const size_t M = std::min((size_t)ctx->maxCand, ctx->dirtyCand);
@@ -289,7 +292,7 @@ static int clear_state(kgmt_ctx* ctx, bool sync) {
     ctx->dirtyTree = 0; ctx->dirtyCand = 0;
     /* scalars: keep the scan epoch monotone across resets */
     DevState z{};
-    z.goalIdx = -1; z.goalBest = ~0ull; z.stop = STOP_ITER_LIMIT;
+    z.goalIdx = -1; z.goalSlot = -1; z.goalBest = ~0ull; z.stop = STOP_ITER_LIMIT; z.itr = 1;
     z.forceChildren = ctx->hState->forceChildren;
     ctx->resetState = z;
     CU(cudaMemcpyAsync(ctx->dState, &ctx->resetState, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
@@ -341,7 +344,8 @@ void kgmt_destroy(kgmt_ctx* ctx) {
     cudaFree(ctx->mapSlab); cudaFree(ctx->mapSlabCkpt);
     cudaFree(ctx->candState); cudaFree(ctx->candCtrl); cudaFree(ctx->candParent);
     cudaFree(ctx->candR1); cudaFree(ctx->candR2); cudaFree(ctx->candFlags);
-    cudaFree(ctx->chunkMask); cudaFree(ctx->blockSum); cudaFree(ctx->stageState); cudaFree(ctx->stageCtrl);
+    cudaFree(ctx->chunkMask); cudaFree(ctx->blockSum); cudaFree(ctx->ticket);
+    cudaFree(ctx->stageState); cudaFree(ctx->stageCtrl);
     cudaFree(ctx->dState); cudaFree(ctx->iterLog);
     if (ctx->hState) cudaFreeHost(ctx->hState);
     cudaFree(ctx->dObs); cudaFree(ctx->dCellStart); cudaFree(ctx->dCellItems);
@@ -400,13 +404,15 @@ int kgmt_create(const kgmt_params* p, kgmt_ctx** out) {
     ctx->R1Score[1] = reinterpret_cast<float*>(m); m += c1;
     ctx->R2 = m; m += c2; ctx->R2Valid = m; m += c2; ctx->R2Invalid = m; m += c2;
     ctx->R2Stamp = reinterpret_cast<unsigned*>(m);
-    const size_t chunks = ((size_t)ctx->maxCand + CHUNK - 1) / CHUNK + 1;
-    ctx->numBlocksCap = (chunks + BLK_CHUNKS - 1) / BLK_CHUNKS + 1;
-    CU(cudaMalloc(&ctx->chunkMask, chunks * 4));
-    CU(cudaMalloc(&ctx->blockSum, ctx->numBlocksCap * 4));
-    CU(cudaMalloc(&ctx->stageState, (size_t)ctx->maxCand * 16));
-    CU(cudaMalloc(&ctx->stageCtrl, (size_t)ctx->maxCand * 16));
-    CU(cudaMemsetAsync(ctx->chunkMask, 0, chunks * 4, ctx->stream));
+    ctx->chunksCap = ((size_t)ctx->maxCand + CHUNK - 1) / CHUNK + 1;
+    ctx->blocksCap = (ctx->chunksCap + BLK_CHUNKS - 1) / BLK_CHUNKS + 1;
+    CU(cudaMalloc(&ctx->chunkMask, 2 * ctx->chunksCap * 4));
+    CU(cudaMalloc(&ctx->blockSum, 3 * ctx->blocksCap * 4));
+    CU(cudaMalloc(&ctx->ticket, 4 * 4));
+    CU(cudaMalloc(&ctx->stageState, 2 * (size_t)ctx->maxCand * 16));
+    CU(cudaMalloc(&ctx->stageCtrl, 2 * (size_t)ctx->maxCand * 16));
+    CU(cudaMemsetAsync(ctx->chunkMask, 0, 2 * ctx->chunksCap * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->ticket, 0, 16, ctx->stream));
     CU(cudaMalloc(&ctx->dState, sizeof(DevState)));
     CU(cudaHostAlloc(&ctx->hState, sizeof(DevState), cudaHostAllocDefault));
     memset(ctx->hState, 0, sizeof(DevState));
@@ -609,18 +615,13 @@ int kgmt_set_children(kgmt_ctx* ctx, int children) {
     ctx->hState->forceChildren = children;
     if (ctx->begun && ctx->hState->stop == STOP_RUNNING) {
         /* re-shape the pending iteration */
-        DevState& s = *ctx->hState;
-        const int remaining = ctx->p.max_tree_size - s.treeSize;
-        if (children > 0) {
-            if ((long long)s.frontierCount * children > std::min<long long>(remaining, ctx->maxCand))
-                return fail(ctx, KGMT_ERR_INVALID, "frontier*children exceeds the remaining tree/candidate capacity");
-            s.mode = 4; s.children = children; s.M = s.frontierCount * children;
-        } else if (32LL * s.frontierCount > remaining) {
-            const int it = (int)((float)remaining / (float)s.frontierCount);
-            if (it >= 1) { s.mode = 2; s.children = it; s.M = s.frontierCount * it; }
-            else { s.mode = 3; s.children = 1; s.M = remaining; }
-        } else { s.mode = 1; s.children = 32; s.M = 32 * s.frontierCount; }
-        s.numChunks = (s.M + CHUNK - 1) / CHUNK;
+        DevState& st = *ctx->hState;
+        const int remaining = ctx->p.max_tree_size - st.treeSize;
+        if (children > 0 && (long long)st.frontierCount * children > std::min<long long>(remaining, ctx->maxCand))
+            return fail(ctx, KGMT_ERR_INVALID, "frontier*children exceeds the remaining tree/candidate capacity");
+        int mode, ch, M;
+        expansion_shape(st.frontierCount, st.treeSize, ctx->p.max_tree_size, children, mode, ch, M);
+        st.mode = mode; st.children = ch; st.M = M; st.numChunks = (M + CHUNK - 1) / CHUNK;
     }
     CU(cudaMemcpyAsync(ctx->dState, ctx->hState, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -647,7 +648,12 @@ int kgmt_restore(kgmt_ctx* ctx) {
     if (rc) return rc;
     CU(cudaMemcpyAsync(ctx->mapSlab, ctx->mapSlabCkpt, ctx->mapSlabInts * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     *ctx->hState = ctx->ckptState;
-    ctx->hState->ticket = 0; ctx->hState->ctasDone = 0;
+    {   /* insertion bookkeeping back to "treeSize rows present, scan buffers clean" */
+        const unsigned tk[4] = {(unsigned)(ctx->gridLoop * WARPS), (unsigned)(ctx->gridLoop * WARPS), (unsigned)(ctx->gridLoop * WARPS), 0u};
+        CU(cudaMemcpyAsync(ctx->ticket, tk, 16, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->blockSum, 0, 3 * ctx->blocksCap * 4, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     CU(cudaMemcpyAsync(ctx->dState, ctx->hState, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return KGMT_OK;
@@ -725,7 +731,7 @@ int kgmt_export(kgmt_ctx* ctx, int id, void* h_dst, size_t bytes) {
         case KGMT_ARR_R2VALID: src = ctx->R2Valid; break;
         case KGMT_ARR_R1INVALID: src = ctx->R1Invalid; break;
         case KGMT_ARR_R2INVALID: src = ctx->R2Invalid; break;
-        case KGMT_ARR_R1SCORE: { int rc = fetch_state(ctx); if (rc) return rc; src = ctx->R1Score[ctx->hState->scoreSel & 1]; break; }
+        case KGMT_ARR_R1SCORE: { int rc = fetch_state(ctx); if (rc) return rc; src = ctx->R1Score[ctx->hState->itr & 1]; break; }
         case KGMT_ARR_R1: src = ctx->R1; break;
         case KGMT_ARR_R2: src = ctx->R2; break;
         case KGMT_ARR_U_R1: src = ctx->candR1; break;
@@ -761,7 +767,7 @@ int kgmt_import(kgmt_ctx* ctx, int id, const void* h_src, size_t bytes) {
         case KGMT_ARR_R2VALID: dst = ctx->R2Valid; break;
         case KGMT_ARR_R1INVALID: dst = ctx->R1Invalid; break;
         case KGMT_ARR_R2INVALID: dst = ctx->R2Invalid; break;
-        case KGMT_ARR_R1SCORE: { int rc = fetch_state(ctx); if (rc) return rc; dst = ctx->R1Score[ctx->hState->scoreSel & 1]; break; }
+        case KGMT_ARR_R1SCORE: { int rc = fetch_state(ctx); if (rc) return rc; dst = ctx->R1Score[ctx->hState->itr & 1]; break; }
         case KGMT_ARR_R1: dst = ctx->R1; break;
         case KGMT_ARR_R2: dst = ctx->R2; break;
         default: return KGMT_ERR_INVALID;

@@ -18,10 +18,14 @@
  *              family with global reductions), accept test on the iteration-start
  *              snapshot; accepted candidates are ballot-compacted inside the chunk
  *              into a staging row, the ballot mask is the chunk's scan input
- *   grid barrier
+ *   ONE grid barrier per iteration
  *   phase B  stage 5b ordered insertion: block sums + a 256-wide scan of the chunk
  *            popcounts give every accepted candidate its tree slot in candidate
- *            order; rows move staging -> tree with float4 loads/stores; goal test.
+ *            order; rows move staging -> tree with float4 loads/stores.
+ *            Every CTA advances the planner scalars itself (same inputs, same result),
+ *            so there is no second barrier: the next phase A starts at once and a
+ *            chunk waits (acquire) only for the 256-row tree segment holding its
+ *            parent and for the score buffer of its iteration.
  *
  * Canonical semantics where the reference races: SURVEY.md Appendix B.
  */
@@ -39,22 +43,30 @@ constexpr int TILE = 256;                 /* threads per CTA */
 constexpr int WARPS = TILE / 32;
 constexpr int CHUNK = 32;                 /* candidates per chunk == one warp */
 constexpr int BLK_CHUNKS = 256;           /* chunks per scan block (one per thread of a CTA in phase B) */
-constexpr int SMALL_M = 256;              /* iterations this small run on CTA 0 alone (one grid barrier instead of two) */
 
 enum { STOP_RUNNING = 0, STOP_SOLVED = 1, STOP_TREE_FULL = 2, STOP_ITER_LIMIT = 3, STOP_FRONTIER_EMPTY = 4 };
 enum { COL_GRID_SMEM = 0, COL_GRID_GLOBAL = 1, COL_BRUTE_SMEM = 2, COL_BRUTE_GLOBAL = 3 };
 enum { FLAG_VALID = 1, FLAG_ACCEPT = 2 };
 
-/* device-resident planner scalars (one per context) */
+/* planner scalars.  The first COPIED_WORDS ints are advanced identically by every CTA in shared memory and written
+ * back by CTA 0; the live fields after them are only ever touched in global memory (atomics / flags). */
 struct DevState {
     int treeSize, frontierStart, frontierCount, itr;           /* itr = iteration about to run (1-based) */
-    int stop, goalIdx; float costToGoal; float R1Threshold;
+    int stop, forceChildren; float costToGoal; float R1Threshold;
     int mode, children, M, numChunks;                           /* shape of the iteration about to run */
-    unsigned ticket, ctasDone; int scoreSel; int forceChildren;   /* scoreSel: which R1Score buffer this iteration reads */
-    unsigned long long goalBest;                                /* (cost bits << 32) | tree index, ~0 = none */
+    int lastMode, lastChildren, lastFrontier, lastM;
+    int lastAccepted, lastItr, iterationsDone, goalSlot;        /* goalSlot: candidate slot of the goal node in its iteration */
+    int blocksTotal, pad0;                                      /* scan blocks of all finished iterations (see insertDone) */
     long long expansions;
-    int lastMode, lastChildren, lastFrontier, lastM, lastAccepted, lastItr, iterationsDone, pad;
+    /* ---- live */
+    unsigned long long goalBest;                                /* (cost bits << 32) | candidate slot, ~0 = none (atomicMin) */
+    int goalIdx;                                                /* tree index of the goal node (written by its inserter) */
+    int scoreReady;                                             /* scores of this iteration are complete (release/acquire) */
+    int insertDone;                                             /* scan blocks inserted so far, whole plan (release counter) */
+    int pad1;
 };
+constexpr int COPIED_WORDS = 24;
+static_assert(offsetof(DevState, goalBest) == COPIED_WORDS * 4, "DevState layout");
 
 struct KArgs {
     /* tree, SoA */
@@ -62,21 +74,23 @@ struct KArgs {
     float4* treeCtrl;             /* (a, steering, duration, cost) */
     int*    treeParent;
     /* occupancy maps */
-    int *R1, *R1Valid, *R1Invalid, *R1Avail, *R1Cov; float* R1Score[2];   /* scores: double-buffered (current / next) */
+    int *R1, *R1Valid, *R1Invalid, *R1Avail, *R1Cov; float* R1Score[2];   /* scores: buffer itr&1 */
     int *R2, *R2Valid, *R2Invalid; unsigned* R2Stamp;
     /* per-candidate records (null unless recording) */
     float4* candState; float4* candCtrl; int* candParent; int* candR1; int* candR2; unsigned char* candFlags;
-    /* ordered insertion */
-    unsigned* chunkMask;          /* [chunks] accept ballot of each 32-candidate chunk */
-    int* blockSum;                /* [chunks / 256 + 1] accepted candidates per scan block; zero between iterations */
-    float4* stageState; float4* stageCtrl;   /* [maxCand] accepted rows, compacted inside their chunk */
+    /* ordered insertion: everything indexed by iteration parity / iteration mod 3 */
+    unsigned* chunkMask;          /* [2][chunksCap] accept ballot of each 32-candidate chunk */
+    int* blockSum;                /* [3][blocksCap] accepted candidates per scan block */
+    unsigned* ticket;             /* [3] next chunk to hand out */
+    float4* stageState; float4* stageCtrl;   /* [2][maxCand] accepted rows, compacted inside their chunk */
+    int chunksCap, blocksCap, maxCand, totalWarps;
     DevState* st;
     /* collision */
     const float4* obstacles; int K;
     const int* cellStart; const float4* cellItems; int cullC; float cullInvX, cullInvY; int cellStartInts; int numItems;
     int obsTile;                  /* obstacles per shared-memory tile (stream mode) */
-    unsigned long long* iterLog;  /* [256][8]: per finished iteration {end ns, M<<32|accepted, CTA0: start, phase A done,
-                                     barrier 1 passed, phase B done, barrier 2 passed, -}; null = off */
+    unsigned long long* iterLog;  /* [256][8]: per iteration {advance ns, M<<32|accepted, CTA0: start, phase A done,
+                                     barrier passed, phase B done, 0, 0}; null = off */
     /* parameters */
     float W, H, L, R1Size, R2Size, goalX, goalY, goalR;
     int N, n, c1, numDisc, maxTree, numIterations, useHist;
@@ -172,15 +186,36 @@ __device__ void scores_block(const KArgs& A, float* p /* smem [1024] */, float* 
 }
 
 /* expansion policy, KGMT.cu:151-158 (canonical prefix mode: SURVEY.md App. B #7) */
-__device__ __forceinline__ void expansion_shape(int active, int treeSize, int maxTree, int forceChildren,
-                                                int& mode, int& children, int& M) {
+__host__ __device__ __forceinline__ void expansion_shape(int active, int treeSize, int maxTree, int forceChildren,
+                                                         int& mode, int& children, int& M) {
     const int remaining = maxTree - treeSize;
     if (forceChildren > 0) { mode = 4; children = forceChildren; M = active * forceChildren; return; }
     if (32LL * active > (long long)remaining) {
-        const int it = __float2int_rz(__fdiv_rn((float)remaining, (float)active));
+        const int it = (int)((float)remaining / (float)active);
         if (it >= 1) { mode = 2; children = it; M = active * it; }
         else         { mode = 3; children = 1;  M = remaining; }
     } else { mode = 1; children = 32; M = 32 * active; }
+}
+
+__device__ __forceinline__ int ld_acquire_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_s32(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed_s32(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+/* wait until *p >= want: relaxed polling with back-off, one acquire fence at the end */
+__device__ __forceinline__ void wait_ge(const int* p, int want) {
+    unsigned ns = 64;
+    while (ld_relaxed_s32(p) < want) { __nanosleep(ns); if (ns < 1024) ns <<= 1; }
+    fence_acq_rel();
 }
 
 /* sum of v over the CTA (all TILE threads call; result in every thread) */
@@ -196,63 +231,62 @@ __device__ __forceinline__ int block_sum(int v, int* sRed /* [WARPS] */) {
     return t;
 }
 
-/* end of an iteration: executed by every thread of ONE CTA after all insertions are visible.
- * KGMT.cu:249-259 + the next iteration's :119-136. */
-__device__ void finalize_iteration(const KArgs& A, float* p, int* sRed, bool withScores) {
-    volatile DevState* st = A.st;
-    __shared__ int sRun, sSel;
-    const int numBlocks = (st->numChunks + BLK_CHUNKS - 1) / BLK_CHUNKS;
-    int mine = 0;
-    for (int b = threadIdx.x; b < numBlocks; b += TILE) { mine += __ldcg(&A.blockSum[b]); A.blockSum[b] = 0; }
-    const int accepted = block_sum(mine, sRed);
-    if (threadIdx.x == 0) {
-        const int M = st->M;
-        if (A.iterLog && st->iterationsDone < 255) {
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            A.iterLog[8 * st->iterationsDone] = t;
-            A.iterLog[8 * st->iterationsDone + 1] = ((unsigned long long)(unsigned)M << 32) | (unsigned)accepted;
-        }
-        st->lastMode = st->mode; st->lastChildren = st->children; st->lastFrontier = st->frontierCount;
-        st->lastM = M; st->lastAccepted = accepted; st->lastItr = st->itr;
-        st->iterationsDone += 1;
-        st->expansions += M;
-        st->frontierStart = st->treeSize;
-        st->frontierCount = accepted;
-        st->treeSize += accepted;                                                   /* :249 */
-        const unsigned long long gb = st->goalBest;
-        if (gb != ~0ull) { st->costToGoal = __uint_as_float((unsigned)(gb >> 32)); st->goalIdx = (int)(unsigned)gb; }
-        int stop = STOP_RUNNING;
-        if (st->costToGoal != 0.0f)             stop = STOP_SOLVED;                 /* :252 */
-        else if (st->treeSize >= A.maxTree)     stop = STOP_TREE_FULL;              /* :255 */
-        else if (accepted == 0)                 stop = STOP_FRONTIER_EMPTY;
-        else if (st->itr >= A.numIterations)    stop = STOP_ITER_LIMIT;             /* :118 */
-        st->stop = stop;
-        if (stop == STOP_RUNNING) {
-            st->itr += 1;                                                           /* :119 */
-            int mode, children, Mn;
-            const int ts = st->treeSize, fc = st->forceChildren;
-            expansion_shape(accepted, ts, A.maxTree, fc, mode, children, Mn);
-            st->mode = mode; st->children = children; st->M = Mn; st->numChunks = (Mn + CHUNK - 1) / CHUNK;
-        }
-        st->ticket = 0; st->ctasDone = 0;
-        sRun = (stop == STOP_RUNNING);
-        sSel = st->scoreSel;
-        if (sRun) st->scoreSel = sSel ^ 1;             /* the next iteration reads the scores of the maps as they are now */
+/* end of an iteration, KGMT.cu:249-259 + the next iteration's :119: pure function of (S, accepted, goalBest),
+ * evaluated by thread 0 of EVERY CTA on its own copy. */
+__device__ __forceinline__ void advance_state(const KArgs& A, DevState& S, int accepted, unsigned long long gb) {
+    S.lastMode = S.mode; S.lastChildren = S.children; S.lastFrontier = S.frontierCount;
+    S.lastM = S.M; S.lastAccepted = accepted; S.lastItr = S.itr;
+    S.iterationsDone += 1;
+    S.blocksTotal += (S.numChunks + BLK_CHUNKS - 1) / BLK_CHUNKS;
+    S.expansions += S.M;
+    S.frontierStart = S.treeSize;
+    S.frontierCount = accepted;
+    S.treeSize += accepted;                                                         /* :249 */
+    if (gb != ~0ull && S.costToGoal == 0.0f) {                                      /* canonical min-cost goal (App. B #5) */
+        S.costToGoal = __uint_as_float((unsigned)(gb >> 32));
+        S.goalSlot = (int)(unsigned)gb;
     }
-    __syncthreads();
-    if (withScores && sRun) scores_block(A, p, A.R1Score[sSel ^ 1]);
-    __threadfence();
+    int stop = STOP_RUNNING;
+    if (S.costToGoal != 0.0f)              stop = STOP_SOLVED;                      /* :252 */
+    else if (S.treeSize >= A.maxTree)      stop = STOP_TREE_FULL;                   /* :255 */
+    else if (accepted == 0)                stop = STOP_FRONTIER_EMPTY;
+    else if (S.itr >= A.numIterations)     stop = STOP_ITER_LIMIT;                  /* :118 */
+    S.stop = stop;
+    if (stop == STOP_RUNNING) {
+        S.itr += 1;                                                                 /* :119 */
+        int mode, children, Mn;
+        expansion_shape(accepted, S.treeSize, A.maxTree, S.forceChildren, mode, children, Mn);
+        S.mode = mode; S.children = children; S.M = Mn; S.numChunks = (Mn + CHUNK - 1) / CHUNK;
+    }
 }
 
-/* per-iteration scalars, read once by every thread */
-struct IterView { int itr, treeSize, frontierStart, children, M, numChunks; uint32_t key0; const float* score; float* scoreNext; };
+/* per-iteration view, identical on every thread */
+struct IterView {
+    int itr, treeSize, frontierStart, children, M, numChunks; uint32_t key0;
+    const float* score;                      /* R1 scores of this iteration */
+    unsigned* chunkMask; int* blockSum; float4* stageState; float4* stageCtrl;   /* this iteration's buffers */
+    int goalSlot;                            /* >= 0: this iteration produced the goal node at that candidate slot */
+};
+
+__device__ __forceinline__ IterView make_view(const KArgs& A, const DevState& S) {
+    IterView it;
+    it.itr = S.itr; it.treeSize = S.treeSize; it.frontierStart = S.frontierStart; it.children = S.children;
+    it.M = S.M; it.numChunks = S.numChunks; it.key0 = A.seed + (uint32_t)S.itr;
+    it.score = A.R1Score[S.itr & 1];
+    it.chunkMask = A.chunkMask + (size_t)(S.itr & 1) * A.chunksCap;
+    it.blockSum = A.blockSum + (size_t)(S.itr % 3) * A.blocksCap;
+    it.stageState = A.stageState + (size_t)(S.itr & 1) * A.maxCand;
+    it.stageCtrl = A.stageCtrl + (size_t)(S.itr & 1) * A.maxCand;
+    it.goalSlot = -1;
+    return it;
+}
 
 /* ---------------------------------------------------------------- phase A: one chunk ---
- * 32 candidates, one per lane: stages 2-5a.  No communication outside the warp. */
+ * 32 candidates, one per lane: stages 2-5a.  No communication outside the warp.
+ * scoresOk (warp-uniform) remembers that this iteration's score buffer has been seen complete. */
 template <class Collide, bool RECORD>
 __device__ __forceinline__ void expand_chunk(const KArgs& A, const IterView& it, const DynParams& dyn,
-                                             const Collide& col, int c, int lane, int* hV, int* hI) {
+                                             const Collide& col, int c, int lane, int* hV, int* hI, bool& scoresOk) {
     const int s = c * CHUNK + lane;
     const bool live = s < it.M;
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -262,47 +296,53 @@ __device__ __forceinline__ void expand_chunk(const KArgs& A, const IterView& it,
     float parentCost = 0.f;
     if (live) {
         parent = it.frontierStart + s / it.children;                       /* KGMT.cu:374-376 / :454 */
-        x = __ldcg(&A.treeState[parent]);                                  /* L2-coherent: written by other SMs last iteration */
+        x = __ldcg(&A.treeState[parent]);                                  /* L2-coherent: written by other SMs */
         parentCost = __ldcg(&A.treeCtrl[parent]).w;
         u = sample_controls((uint32_t)s, it.key0);
         valid = propagate_edge(x, u, dyn, col);
         r1 = region_r1(x.x, x.y, A.R1Size, A.N);                           /* KGMT.cu:390 */
         r2 = region_r2(x.x, x.y, r1, A.R1Size, A.N, A.R2Size, A.n);        /* KGMT.cu:391 */
-        /* maps + accept, KGMT.cu:392-411 on the iteration-start snapshot (App. B #1,#2) */
-        if (r1 >= 0) {
-            if (valid) {
-                accept = u.u3 <= __ldcg(&it.score[r1]);
-                if (r2 >= 0) {
-                    const unsigned stamp = __ldcg(&A.R2Stamp[r2]);
-                    if (stamp == 0u || stamp > (unsigned)it.itr) accept = true;    /* unavailable at iteration start */
-                    if (stamp == 0u) {
-                        if (atomicCAS(&A.R2Stamp[r2], 0u, (unsigned)it.itr + 1u) == 0u) atomicAdd(&A.R1Cov[r1], 1);
-                    }
-                    atomicAdd(&A.R2Valid[r2], 1);
+    }
+    if (!scoresOk) {                /* scores of this iteration (and hence the maps of the previous one) are final */
+        wait_ge(&A.st->scoreReady, it.itr);
+        scoresOk = true;
+    }
+    if (live && r1 >= 0) {          /* maps + accept, KGMT.cu:392-411 on the iteration-start snapshot (App. B #1,#2) */
+        if (valid) {
+            accept = u.u3 <= __ldcg(&it.score[r1]);
+            if (r2 >= 0) {
+                const unsigned stamp = __ldcg(&A.R2Stamp[r2]);
+                if (stamp == 0u || stamp > (unsigned)it.itr) accept = true;        /* unavailable at iteration start */
+                if (stamp == 0u) {
+                    if (atomicCAS(&A.R2Stamp[r2], 0u, (unsigned)it.itr + 1u) == 0u) atomicAdd(&A.R1Cov[r1], 1);
                 }
-            } else if (r2 >= 0) {
-                atomicAdd(&A.R2Invalid[r2], 1);
+                atomicAdd(&A.R2Valid[r2], 1);
             }
-            if (r2 >= 0) atomicAdd(&A.R2[r2], 1);
-            if (A.useHist) {
-                atomicAdd(valid ? &hV[r1] : &hI[r1], 1);
-            } else {
-                atomicAdd(&A.R1[r1], 1);
-                if (valid) { atomicAdd(&A.R1Valid[r1], 1); A.R1Avail[r1] = 1; }
-                else atomicAdd(&A.R1Invalid[r1], 1);
-            }
+        } else if (r2 >= 0) {
+            atomicAdd(&A.R2Invalid[r2], 1);
+        }
+        if (r2 >= 0) atomicAdd(&A.R2[r2], 1);
+        if (A.useHist) {
+            atomicAdd(valid ? &hV[r1] : &hI[r1], 1);
+        } else {
+            atomicAdd(&A.R1[r1], 1);
+            if (valid) { atomicAdd(&A.R1Valid[r1], 1); A.R1Avail[r1] = 1; }
+            else atomicAdd(&A.R1Invalid[r1], 1);
         }
     }
     /* ballot compaction inside the chunk; the mask is the input of the ordered scan (phase B) */
     const unsigned bal = __ballot_sync(0xffffffffu, accept);
     if (accept) {
         const int at = c * CHUNK + __popc(bal & ((1u << lane) - 1u));
-        __stcg(&A.stageState[at], x);
-        __stcg(&A.stageCtrl[at], make_float4(u.a, u.steering, u.duration, __fadd_rn(parentCost, u.duration)));  /* :585-586 */
+        const float cost = __fadd_rn(parentCost, u.duration);                      /* :585-586, :631-633 */
+        __stcg(&it.stageState[at], x);
+        __stcg(&it.stageCtrl[at], make_float4(u.a, u.steering, u.duration, cost));
+        if (in_goal(x.x, x.y, A.goalX, A.goalY, A.goalR))                          /* :589; min cost, then first in order */
+            atomicMin(&A.st->goalBest, ((unsigned long long)__float_as_uint(cost) << 32) | (unsigned)s);
     }
     if (lane == 0) {
-        __stcg(&A.chunkMask[c], bal);
-        if (bal) atomicAdd(&A.blockSum[c / BLK_CHUNKS], __popc(bal));
+        __stcg(&it.chunkMask[c], bal);
+        if (bal) atomicAdd(&it.blockSum[c / BLK_CHUNKS], __popc(bal));
     }
     if (RECORD && live) {
         A.candState[s] = x;
@@ -322,7 +362,7 @@ __device__ __forceinline__ void expand_chunk(const KArgs& A, const IterView& it,
 __device__ __forceinline__ void insert_block(const KArgs& A, const IterView& it, int blk, int base, int* sScan /* [WARPS] */) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blk * BLK_CHUNKS + tid;
-    const unsigned mask = (c < it.numChunks) ? __ldcg(&A.chunkMask[c]) : 0u;
+    const unsigned mask = (c < it.numChunks) ? __ldcg(&it.chunkMask[c]) : 0u;
     const int cnt = __popc(mask);
     int incl = cnt;
 #pragma unroll
@@ -351,32 +391,43 @@ __device__ __forceinline__ void insert_block(const KArgs& A, const IterView& it,
             const int r = q - excl;
             const int bit = (int)__fns(m, 0, r + 1);
             const int ci = c0 + i;
-            const float4 x = __ldcg(&A.stageState[ci * CHUNK + r]);
-            const float4 u = __ldcg(&A.stageCtrl[ci * CHUNK + r]);
+            const int slot = ci * CHUNK + bit;
+            const float4 x = __ldcg(&it.stageState[ci * CHUNK + r]);
+            const float4 u = __ldcg(&it.stageCtrl[ci * CHUNK + r]);
             const int dst = dst0 + q;
             A.treeState[dst] = x;
             A.treeCtrl[dst] = u;
-            A.treeParent[dst] = it.frontierStart + (ci * CHUNK + bit) / it.children;
-            if (in_goal(x.x, x.y, A.goalX, A.goalY, A.goalR))              /* :589; canonical min (App. B #5) */
-                atomicMin(&A.st->goalBest, ((unsigned long long)__float_as_uint(u.w) << 32) | (unsigned)dst);
+            A.treeParent[dst] = it.frontierStart + slot / it.children;
+            if (slot == it.goalSlot) A.st->goalIdx = dst;
         }
     }
+    /* announce the block: the next phase A starts without a barrier and waits on this counter */
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicAdd(&A.st->insertDone, 1);
 }
 
-/* ------------------------------------------------------------------ the planner kernel --
- * Cooperative launch, grid = resident CTAs.  Runs up to maxIters expansion iterations
- * (1 = kgmt_expand_iteration, numIterations = kgmt_plan) or until the planner stops. */
-template <int COL, bool RECORD>
-__global__ void __launch_bounds__(TILE) expand_kernel(const KArgs A, int maxIters) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+/* the group of CTAs that plans one query together */
+struct GridGroup {
+    cg::grid_group g; int rank, size;
+    __device__ GridGroup() : g(cg::this_grid()), rank((int)blockIdx.x), size((int)gridDim.x) {}
+    __device__ __forceinline__ void sync() { g.sync(); }
+};
+
+/* ------------------------------------------------------------------ the planner loop ---
+ * Runs up to maxIters expansion iterations (1 = kgmt_expand_iteration, all = kgmt_plan) or until
+ * the planner stops, on the CTAs of `grp` (all co-resident). */
+template <int COL, bool RECORD, class Group>
+__device__ void run_plan(const KArgs& A, int maxIters, Group& grp, unsigned char* smem_raw) {
     __shared__ __align__(8) uint64_t sBar;
     __shared__ int sRed[WARPS];
-    __shared__ int sLast;
     __shared__ float sP[1024];
+    __shared__ DevState S;
+    __shared__ int sAccepted;
+    __shared__ unsigned long long sGoalBest;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     DevState* st = A.st;
-    cg::grid_group grid = cg::this_grid();
 
     /* shared-memory carve-up: [R1 histograms][collision data] */
     int* hV = reinterpret_cast<int*>(smem_raw);
@@ -414,106 +465,117 @@ __global__ void __launch_bounds__(TILE) expand_kernel(const KArgs A, int maxIter
     const CollideSmemAll colAllS{sObs, A.K};
     const CollideSmemAll colAllG{A.obstacles, A.K};
 
-    auto run_chunk = [&](const IterView& it, int c) {
-        if (COL == COL_GRID_SMEM)        expand_chunk<CollideGrid, RECORD>(A, it, dyn, colGridS, c, lane, hV, hI);
-        else if (COL == COL_GRID_GLOBAL) expand_chunk<CollideGrid, RECORD>(A, it, dyn, colGridG, c, lane, hV, hI);
-        else if (COL == COL_BRUTE_SMEM)  expand_chunk<CollideSmemAll, RECORD>(A, it, dyn, colAllS, c, lane, hV, hI);
-        else                             expand_chunk<CollideSmemAll, RECORD>(A, it, dyn, colAllG, c, lane, hV, hI);
-    };
-    auto flush_hist = [&]() {          /* R1 = R1Valid + R1Invalid increments, KGMT.cu:392,406,409 */
-        if (!A.useHist) return;
-        for (int c = tid; c < A.c1; c += TILE) {
-            const int v = hV[c], iv = hI[c];
-            if (v | iv) {
-                atomicAdd(&A.R1[c], v + iv);
-                if (v) { atomicAdd(&A.R1Valid[c], v); A.R1Avail[c] = 1; }
-                if (iv) atomicAdd(&A.R1Invalid[c], iv);
-            }
-        }
-    };
+    /* every CTA keeps its own copy of the planner scalars */
+    if (tid < COPIED_WORDS) reinterpret_cast<int*>(&S)[tid] = __ldcg(reinterpret_cast<const int*>(st) + tid);
+    __syncthreads();
+
+    const int totalWarps = grp.size * WARPS;
+    const int gw = grp.rank * WARPS + warp;
+    const int scoreRank = grp.size - 1;
+    const int resetRank = grp.size > 1 ? grp.size - 2 : 0;
 
     for (int iter = 0; iter < maxIters; ++iter) {
-        /* iteration scalars (written by the previous finalize, ordered by the launch boundary or the grid barrier) */
-        if (*(volatile int*)&st->stop != STOP_RUNNING) break;
-        IterView it;
-        it.itr = *(volatile int*)&st->itr;
-        it.treeSize = *(volatile int*)&st->treeSize;
-        it.frontierStart = *(volatile int*)&st->frontierStart;
-        it.children = *(volatile int*)&st->children;
-        it.M = *(volatile int*)&st->M;
-        it.numChunks = *(volatile int*)&st->numChunks;
-        it.key0 = A.seed + (uint32_t)it.itr;
-        { const int sel = *(volatile int*)&st->scoreSel; it.score = A.R1Score[sel]; it.scoreNext = A.R1Score[sel ^ 1]; }
-        const int logRow = *(volatile int*)&st->iterationsDone;
-        auto stamp = [&](int col) {
-            if (A.iterLog && blockIdx.x == 0 && tid == 0 && logRow < 255) {
+        if (S.stop != STOP_RUNNING) break;
+        IterView it = make_view(A, S);
+        const int logRow = S.iterationsDone;
+        auto stamp = [&](int colIdx) {
+            if (A.iterLog && grp.rank == 0 && tid == 0 && logRow < 255) {
                 unsigned long long t;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                A.iterLog[8 * logRow + col] = t;
+                A.iterLog[8 * logRow + colIdx] = t;
             }
         };
         stamp(2);
 
-        if (it.M <= SMALL_M) {
-            /* latency path: the whole iteration on CTA 0, one chunk per warp, CTA barriers only */
-            if (blockIdx.x == 0) {
-                if (A.useHist) for (int c = tid; c < 2 * A.c1; c += TILE) hV[c] = 0;
-                __syncthreads();
-                if (warp < it.numChunks) run_chunk(it, warp);
-                __syncthreads();
-                stamp(3);
-                flush_hist();
-                insert_block(A, it, 0, 0, sRed);
-                __threadfence();
-                __syncthreads();
-                stamp(5);
-                finalize_iteration(A, sP, sRed, true);
-            }
-            grid.sync();
-            stamp(6);
-            continue;
-        }
-
-        /* ---- phase A: chunks handed out by ticket, next ticket prefetched behind the current chunk */
+        /* ---- phase A: first chunk by position, further chunks by ticket (prefetched behind the current chunk) */
         if (A.useHist) for (int c = tid; c < 2 * A.c1; c += TILE) hV[c] = 0;
         __syncthreads();
         {
+            bool scoresOk = false;
+            unsigned* ticket = A.ticket + (it.itr % 3);
+            int c = gw;
             int t = 0;
-            if (lane == 0) t = (int)atomicAdd(&st->ticket, 1u);
-            int c = __shfl_sync(0xffffffffu, t, 0);
+            /* parents were inserted by the previous phase B, possibly still running on other CTAs */
+            if (c < it.numChunks) wait_ge(&st->insertDone, S.blocksTotal);
             while (c < it.numChunks) {
-                if (lane == 0) t = (int)atomicAdd(&st->ticket, 1u);
-                run_chunk(it, c);
+                if (lane == 0) t = (int)atomicAdd(ticket, 1u);
+                if (COL == COL_GRID_SMEM)        expand_chunk<CollideGrid, RECORD>(A, it, dyn, colGridS, c, lane, hV, hI, scoresOk);
+                else if (COL == COL_GRID_GLOBAL) expand_chunk<CollideGrid, RECORD>(A, it, dyn, colGridG, c, lane, hV, hI, scoresOk);
+                else if (COL == COL_BRUTE_SMEM)  expand_chunk<CollideSmemAll, RECORD>(A, it, dyn, colAllS, c, lane, hV, hI, scoresOk);
+                else                             expand_chunk<CollideSmemAll, RECORD>(A, it, dyn, colAllG, c, lane, hV, hI, scoresOk);
                 c = __shfl_sync(0xffffffffu, t, 0);
             }
         }
         __syncthreads();
-        flush_hist();
+        if (A.useHist) {               /* R1 = R1Valid + R1Invalid increments, KGMT.cu:392,406,409 */
+            for (int c = tid; c < A.c1; c += TILE) {
+                const int v = hV[c], iv = hI[c];
+                if (v | iv) {
+                    atomicAdd(&A.R1[c], v + iv);
+                    if (v) { atomicAdd(&A.R1Valid[c], v); A.R1Avail[c] = 1; }
+                    if (iv) atomicAdd(&A.R1Invalid[c], iv);
+                }
+            }
+        }
         stamp(3);
-        grid.sync();
+        grp.sync();                    /* the one barrier: all ballots, block sums, maps and the goal minimum are final */
         stamp(4);
 
-        /* ---- the next iteration's R1 scores (maps are final now) on the CTA least likely to own a scan block,
-         *      overlapped with phase B.  If the planner stops in this iteration they are simply not used. */
-        if (blockIdx.x == gridDim.x - 1) scores_block(A, sP, it.scoreNext);
+        /* ---- every CTA advances the planner scalars on its own copy */
+        const int numBlocks = (it.numChunks + BLK_CHUNKS - 1) / BLK_CHUNKS;
+        {
+            int mine = 0;
+            for (int b = tid; b < numBlocks; b += TILE) mine += __ldcg(&it.blockSum[b]);
+            const int accepted = block_sum(mine, sRed);
+            if (tid == 0) {
+                sGoalBest = *(volatile unsigned long long*)&st->goalBest;
+                const bool hadGoal = S.costToGoal != 0.0f;
+                advance_state(A, S, accepted, sGoalBest);
+                sAccepted = (!hadGoal && S.costToGoal != 0.0f) ? S.goalSlot : -1;
+                if (grp.rank == 0 && A.iterLog && logRow < 255) {
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    A.iterLog[8 * logRow] = t;
+                    A.iterLog[8 * logRow + 1] = ((unsigned long long)(unsigned)it.M << 32) | (unsigned)accepted;
+                }
+            }
+            __syncthreads();
+            it.goalSlot = sAccepted;
+        }
+
+        /* ---- housekeeping spread over otherwise idle CTAs (all of it is consumed after a later barrier or flag) */
+        if (grp.rank == scoreRank && S.stop == STOP_RUNNING) {
+            /* next iteration's R1 scores from the now-final maps, then publish them */
+            scores_block(A, sP, A.R1Score[S.itr & 1]);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release_s32(&st->scoreReady, S.itr);
+        }
+        if (grp.rank == resetRank) {
+            /* recycle the ticket and block sums last used by the previous iteration (next used two iterations from now) */
+            const int r = (it.itr + 2) % 3;
+            for (int b = tid; b < A.blocksCap; b += TILE) A.blockSum[(size_t)r * A.blocksCap + b] = 0;
+            if (tid == 0) A.ticket[r] = (unsigned)totalWarps;
+        }
+        if (grp.rank == 0 && tid < COPIED_WORDS)            /* for the host and for the next launch */
+            reinterpret_cast<int*>(st)[tid] = reinterpret_cast<const int*>(&S)[tid];
 
         /* ---- phase B: ordered insertion, scan blocks strided over the CTAs */
-        const int numBlocks = (it.numChunks + BLK_CHUNKS - 1) / BLK_CHUNKS;
-        for (int blk = blockIdx.x; blk < numBlocks; blk += gridDim.x) {
+        for (int blk = grp.rank; blk < numBlocks; blk += grp.size) {
             int mine = 0;
-            for (int b = tid; b < blk; b += TILE) mine += __ldcg(&A.blockSum[b]);
+            for (int b = tid; b < blk; b += TILE) mine += __ldcg(&it.blockSum[b]);
             const int base = block_sum(mine, sRed);
             insert_block(A, it, blk, base, sRed);
         }
-        __threadfence();
-        __syncthreads();
         stamp(5);
-        if (tid == 0) sLast = (atomicAdd(&st->ctasDone, 1u) == gridDim.x - 1u);
-        __syncthreads();
-        if (sLast) { __threadfence(); finalize_iteration(A, sP, sRed, false); }
-        grid.sync();
-        stamp(6);
     }
+}
+
+template <int COL, bool RECORD>
+__global__ void __launch_bounds__(TILE) expand_kernel(const KArgs A, int maxIters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GridGroup grp;
+    run_plan<COL, RECORD, GridGroup>(A, maxIters, grp, smem_raw);
 }
 
 /* -------------------------------------------- stages 2-4 alone (parity / sweeps) -------
@@ -591,10 +653,10 @@ __global__ void __launch_bounds__(TILE) begin_kernel(const KArgs A, float4 rootS
         if (r1 >= 0) { A.R1[r1] = 1; A.R1Avail[r1] = 1; A.R1Valid[r1] = 1; }       /* :94,95,97 */
         if (r2 >= 0 && A.R2Stamp[r2] == 0u) { A.R2Stamp[r2] = 1u; A.R1Cov[r1] += 1; }  /* :96 */
         st->treeSize = 1; st->frontierStart = 0; st->frontierCount = 1; st->itr = 1;
-        st->goalIdx = -1; st->costToGoal = 0.0f; st->goalBest = ~0ull;
-        st->expansions = 0; st->iterationsDone = 0;
+        st->goalIdx = -1; st->goalSlot = -1; st->costToGoal = 0.0f; st->goalBest = ~0ull;
+        st->expansions = 0; st->iterationsDone = 0; st->blocksTotal = 0; st->insertDone = 0;
         st->lastMode = st->lastChildren = st->lastFrontier = st->lastM = st->lastAccepted = st->lastItr = 0;
-        st->ticket = 0; st->ctasDone = 0; st->scoreSel = 0;
+        A.ticket[0] = A.ticket[1] = A.ticket[2] = (unsigned)A.totalWarps;
         int stop = STOP_RUNNING;
         if (A.numIterations <= 0) stop = STOP_ITER_LIMIT;
         else if (1 >= A.maxTree) stop = STOP_TREE_FULL;
@@ -604,7 +666,10 @@ __global__ void __launch_bounds__(TILE) begin_kernel(const KArgs A, float4 rootS
         st->mode = mode; st->children = children; st->M = M; st->numChunks = (M + CHUNK - 1) / CHUNK;
     }
     __syncthreads();
-    scores_block(A, sP, A.R1Score[0]);
+    scores_block(A, sP, A.R1Score[1]);              /* iteration 1 reads buffer 1 & 1 */
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_s32(&st->scoreReady, 1);
 }
 
 /* kgmt_seed_frontier: `count` nodes already copied into tree[0,count); all are frontier */
@@ -623,10 +688,10 @@ __global__ void __launch_bounds__(TILE) seed_finish_kernel(const KArgs A, int co
     DevState* st = A.st;
     if (threadIdx.x == 0) {
         st->treeSize = count; st->frontierStart = 0; st->frontierCount = count; st->itr = 1;
-        st->goalIdx = -1; st->costToGoal = 0.0f; st->goalBest = ~0ull;
-        st->expansions = 0; st->iterationsDone = 0;
+        st->goalIdx = -1; st->goalSlot = -1; st->costToGoal = 0.0f; st->goalBest = ~0ull;
+        st->expansions = 0; st->iterationsDone = 0; st->blocksTotal = 0; st->insertDone = 0;
         st->lastMode = st->lastChildren = st->lastFrontier = st->lastM = st->lastAccepted = st->lastItr = 0;
-        st->ticket = 0; st->ctasDone = 0; st->scoreSel = 0;
+        A.ticket[0] = A.ticket[1] = A.ticket[2] = (unsigned)A.totalWarps;
         int stop = STOP_RUNNING;
         if (A.numIterations <= 0) stop = STOP_ITER_LIMIT;
         else if (count >= A.maxTree) stop = STOP_TREE_FULL;
@@ -635,8 +700,10 @@ __global__ void __launch_bounds__(TILE) seed_finish_kernel(const KArgs A, int co
         if (stop == STOP_RUNNING) expansion_shape(count, count, A.maxTree, st->forceChildren, mode, children, M);
         st->mode = mode; st->children = children; st->M = M; st->numChunks = (M + CHUNK - 1) / CHUNK;
     }
+    scores_block(A, sP, A.R1Score[1]);
+    __threadfence();
     __syncthreads();
-    scores_block(A, sP, A.R1Score[0]);
+    if (threadIdx.x == 0) st_release_s32(&st->scoreReady, 1);
 }
 
 /* R1Cov[c] = number of available R2 cells of R1 cell c (after import / seeding) */
@@ -655,7 +722,7 @@ __global__ void recount_cov_kernel(const KArgs A) {
 
 __global__ void __launch_bounds__(TILE) scores_kernel(const KArgs A) {
     __shared__ float sP[1024];
-    scores_block(A, sP, A.R1Score[A.st->scoreSel]);
+    scores_block(A, sP, A.R1Score[A.st->itr & 1]);
 }
 
 /* views in the reference's element layout (export) */
