@@ -67,6 +67,16 @@ struct kgmt_ctx {
     long long launches = 0;
     int planLaunches = 0;
     size_t dirtyTree = 0, dirtyCand = 0;   /* rows a plan may have written since the last clear */
+    /* batched planning workspaces (kgmt_plan_batch) */
+    struct Batch {
+        int numWs = 0, clusterSize = 0, Qcap = 0, maxPath = 0;
+        float4 *treeState = nullptr, *treeCtrl = nullptr, *stageState = nullptr, *stageCtrl = nullptr;
+        int *treeParent = nullptr, *mapSlab = nullptr, *blockSum = nullptr, *queryTicket = nullptr, *wsQuery = nullptr, *pathLen = nullptr;
+        unsigned *chunkMask = nullptr, *ticket = nullptr;
+        float4 *initState = nullptr, *initCtrl = nullptr; float2* goalXY = nullptr; uint32_t* seeds = nullptr;
+        DevState* states = nullptr; float* paths = nullptr;
+        size_t mapIntsStride = 0;
+    } batch;
     unsigned epochBase = 0;
     DevState resetState{};
     char err[512] = {0};
@@ -320,6 +330,25 @@ static void fill_result(const kgmt_ctx* ctx, kgmt_result* out, float ms) {
     out->device_ms = ms; out->kernel_launches = ctx->planLaunches;
 }
 
+typedef void (*batch_fn)(const BatchArgs);
+static batch_fn batch_entry(int col) {
+    switch (col) {
+        case COL_GRID_SMEM: return batch_kernel<COL_GRID_SMEM>;
+        case COL_GRID_GLOBAL: return batch_kernel<COL_GRID_GLOBAL>;
+        case COL_BRUTE_SMEM: return batch_kernel<COL_BRUTE_SMEM>;
+        default: return batch_kernel<COL_BRUTE_GLOBAL>;
+    }
+}
+static void free_batch(kgmt_ctx* ctx) {
+    kgmt_ctx::Batch& b = ctx->batch;
+    cudaFree(b.treeState); cudaFree(b.treeCtrl); cudaFree(b.stageState); cudaFree(b.stageCtrl); cudaFree(b.treeParent);
+    cudaFree(b.mapSlab); cudaFree(b.blockSum); cudaFree(b.queryTicket); cudaFree(b.wsQuery); cudaFree(b.pathLen);
+    cudaFree(b.chunkMask); cudaFree(b.ticket); cudaFree(b.initState); cudaFree(b.initCtrl); cudaFree(b.goalXY);
+    cudaFree(b.seeds); cudaFree(b.states); cudaFree(b.paths);
+    b = kgmt_ctx::Batch();
+}
+
+
 /* ================================================================================ ABI == */
 extern "C" {
 
@@ -350,6 +379,7 @@ void kgmt_destroy(kgmt_ctx* ctx) {
     if (ctx->hState) cudaFreeHost(ctx->hState);
     cudaFree(ctx->dObs); cudaFree(ctx->dCellStart); cudaFree(ctx->dCellItems);
     cudaFree(ctx->scratch); cudaFree(ctx->dParents);
+    free_batch(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -535,6 +565,98 @@ int kgmt_plan(kgmt_ctx* ctx, const float* initial7, const float* goal7, kgmt_res
     CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (out) fill_result(ctx, out, ms);
     return KGMT_OK;
+}
+
+/* ---- batched planning: Q independent queries on the context's map (BASELINE config 4) ------------------------- */
+int kgmt_plan_batch(kgmt_ctx* ctx, const float* h_inits7, const float* h_goals7, const uint32_t* h_seeds, int Q,
+                    int cluster_size, kgmt_result* out, float* h_paths7, int max_path, int* h_path_len, float* device_ms) {
+    if (!ctx || !h_inits7 || !h_goals7 || !h_seeds || Q < 1) return fail(ctx, KGMT_ERR_INVALID, "bad batch arguments");
+    if (cluster_size != 1 && cluster_size != 2 && cluster_size != 4 && cluster_size != 8)
+        return fail(ctx, KGMT_ERR_INVALID, "cluster_size must be 1, 2, 4 or 8");
+    if (h_paths7 && (max_path < 1 || !h_path_len)) return fail(ctx, KGMT_ERR_INVALID, "paths need max_path and path_len");
+    CU(cudaSetDevice(ctx->device));
+    kgmt_ctx::Batch& b = ctx->batch;
+    batch_fn f = batch_entry(ctx->col);
+    CU(cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemBytes));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(TILE); cfg.dynamicSmemBytes = ctx->smemBytes; cfg.stream = ctx->stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(cluster_size * 8);
+    int maxClusters = 0;
+    CU(cudaOccupancyMaxActiveClusters(&maxClusters, (const void*)f, &cfg));
+    if (maxClusters < 1) return fail(ctx, KGMT_ERR_CUDA, "no cluster of %d CTAs fits", cluster_size);
+    const int numWs = std::min(maxClusters, Q);
+    const size_t T = (size_t)ctx->p.max_tree_size, M = (size_t)ctx->maxCand;
+    const size_t mapStride = (7 * (size_t)ctx->c1 + 4 * ctx->c2 + 3) & ~(size_t)3;
+    const int wantPath = h_paths7 ? max_path : 0;
+    if (numWs > b.numWs || cluster_size != b.clusterSize || Q > b.Qcap || wantPath > b.maxPath) {
+        free_batch(ctx);
+        const size_t W = (size_t)std::max(numWs, 1);
+        CU(cudaMalloc(&b.treeState, W * T * 16)); CU(cudaMalloc(&b.treeCtrl, W * T * 16)); CU(cudaMalloc(&b.treeParent, W * T * 4));
+        CU(cudaMalloc(&b.stageState, W * 2 * M * 16)); CU(cudaMalloc(&b.stageCtrl, W * 2 * M * 16));
+        CU(cudaMalloc(&b.mapSlab, W * mapStride * 4));
+        CU(cudaMalloc(&b.chunkMask, W * 2 * ctx->chunksCap * 4)); CU(cudaMalloc(&b.blockSum, W * 3 * ctx->blocksCap * 4));
+        CU(cudaMalloc(&b.ticket, W * 16)); CU(cudaMalloc(&b.queryTicket, 4)); CU(cudaMalloc(&b.wsQuery, W * 4));
+        CU(cudaMalloc(&b.initState, (size_t)Q * 16)); CU(cudaMalloc(&b.initCtrl, (size_t)Q * 16));
+        CU(cudaMalloc(&b.goalXY, (size_t)Q * 8)); CU(cudaMalloc(&b.seeds, (size_t)Q * 4));
+        CU(cudaMalloc(&b.states, (size_t)Q * sizeof(DevState)));
+        CU(cudaMalloc(&b.pathLen, (size_t)Q * 4));
+        if (wantPath) CU(cudaMalloc(&b.paths, (size_t)Q * wantPath * 28));
+        b.numWs = numWs; b.clusterSize = cluster_size; b.Qcap = Q; b.maxPath = wantPath; b.mapIntsStride = mapStride;
+    }
+    std::vector<float> hs((size_t)Q * 4), hc((size_t)Q * 4), hg((size_t)Q * 2);
+    for (int q = 0; q < Q; ++q) {
+        memcpy(&hs[(size_t)q * 4], &h_inits7[(size_t)q * 7], 16);
+        hc[(size_t)q * 4] = h_inits7[(size_t)q * 7 + 4]; hc[(size_t)q * 4 + 1] = h_inits7[(size_t)q * 7 + 5];
+        hc[(size_t)q * 4 + 2] = h_inits7[(size_t)q * 7 + 6]; hc[(size_t)q * 4 + 3] = 0.f;
+        hg[(size_t)q * 2] = h_goals7[(size_t)q * 7]; hg[(size_t)q * 2 + 1] = h_goals7[(size_t)q * 7 + 1];
+    }
+    cudaStream_t s = ctx->stream;
+    CU(cudaEventRecord(ctx->ev0, s));
+    CU(cudaMemcpyAsync(b.initState, hs.data(), (size_t)Q * 16, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b.initCtrl, hc.data(), (size_t)Q * 16, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b.goalXY, hg.data(), (size_t)Q * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b.seeds, h_seeds, (size_t)Q * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(b.states, 0, (size_t)Q * sizeof(DevState), s));
+    CU(cudaMemsetAsync(b.queryTicket, 0, 4, s));
+    CU(cudaMemsetAsync(b.pathLen, 0, (size_t)Q * 4, s));
+    BatchArgs B{};
+    B.base = make_args(ctx);
+    B.base.treeState = b.treeState; B.base.treeCtrl = b.treeCtrl; B.base.treeParent = b.treeParent;
+    B.base.chunkMask = b.chunkMask; B.base.blockSum = b.blockSum; B.base.ticket = b.ticket;
+    B.base.stageState = b.stageState; B.base.stageCtrl = b.stageCtrl;
+    B.base.candState = nullptr; B.base.candCtrl = nullptr; B.base.candParent = nullptr; B.base.candR1 = nullptr;
+    B.base.candR2 = nullptr; B.base.candFlags = nullptr; B.base.iterLog = nullptr;
+    B.Q = Q; B.numWorkspaces = numWs;
+    B.initState = b.initState; B.initCtrl = b.initCtrl; B.goalXY = b.goalXY; B.seeds = b.seeds; B.states = b.states;
+    B.paths = wantPath ? b.paths : nullptr; B.pathLen = b.pathLen; B.maxPath = wantPath;
+    B.queryTicket = b.queryTicket; B.wsQuery = b.wsQuery;
+    B.treeStride = T; B.mapIntsStride = mapStride; B.chunkStride = 2 * ctx->chunksCap; B.blockStride = 3 * ctx->blocksCap;
+    B.stageStride = 2 * M; B.mapSlab = b.mapSlab; B.c2 = ctx->c2;
+    cfg.gridDim = dim3(numWs * cluster_size);
+    CU(cudaLaunchKernelEx(&cfg, f, B));
+    CU(cudaEventRecord(ctx->ev1, s));
+    ctx->launches += 1;
+    std::vector<DevState> hst((size_t)Q);
+    CU(cudaMemcpyAsync(hst.data(), b.states, (size_t)Q * sizeof(DevState), cudaMemcpyDeviceToHost, s));
+    if (wantPath) {
+        CU(cudaMemcpyAsync(h_paths7, b.paths, (size_t)Q * wantPath * 28, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(h_path_len, b.pathLen, (size_t)Q * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (device_ms) *device_ms = ms;
+    if (out)
+        for (int q = 0; q < Q; ++q) {
+            const DevState& d = hst[q];
+            out[q].stop = d.stop; out[q].iterations = d.iterationsDone; out[q].tree_size = d.treeSize;
+            out[q].cost_to_goal = d.costToGoal; out[q].goal_index = d.goalIdx; out[q].expansions = d.expansions;
+            out[q].device_ms = ms; out[q].kernel_launches = 1;
+        }
+    return numWs;
 }
 
 /* ---- stage-level entry points ------------------------------------------------------------- */

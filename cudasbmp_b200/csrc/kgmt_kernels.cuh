@@ -417,9 +417,55 @@ struct GridGroup {
 /* ------------------------------------------------------------------ the planner loop ---
  * Runs up to maxIters expansion iterations (1 = kgmt_expand_iteration, all = kgmt_plan) or until
  * the planner stops, on the CTAs of `grp` (all co-resident). */
+/* the collision structure as the kernels see it, staged once per launch */
+struct ColSet {
+    CollideGrid gridS, gridG;
+    CollideSmemAll allS, allG;
+    int* hV; int* hI;                       /* per-CTA R1 histograms (shared memory) */
+};
+
+/* carve dynamic shared memory [R1 histograms][collision data] and stage the collision structure into it with
+ * bulk async copies (TMA engine) completing on an mbarrier.  All threads of the CTA call. */
+template <int COL>
+__device__ __forceinline__ ColSet stage_collision(const KArgs& A, unsigned char* smem_raw, uint64_t* sBar) {
+    const int tid = threadIdx.x;
+    ColSet cs;
+    cs.hV = reinterpret_cast<int*>(smem_raw);
+    cs.hI = cs.hV + (A.useHist ? A.c1 : 0);
+    unsigned char* colBase = smem_raw + (A.useHist ? ((2 * A.c1 * 4 + 15) & ~15) : 0);
+    const float4* sObs = nullptr; const int* sCellStart = nullptr; const float4* sItems = nullptr;
+    if (COL == COL_GRID_SMEM || COL == COL_BRUTE_SMEM) {
+        uint32_t bytes0 = 0, bytes1 = 0;
+        if (COL == COL_GRID_SMEM) { bytes0 = (uint32_t)A.cellStartInts * 4u; bytes1 = (uint32_t)A.numItems * 16u; }
+        else                      { bytes0 = (uint32_t)A.K * 16u; }
+        if (tid == 0) { mbar_init(sBar, 1); mbar_fence_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(sBar, bytes0 + bytes1);
+            if (COL == COL_GRID_SMEM) {
+                bulk_g2s_chunked(colBase, A.cellStart, bytes0, sBar);
+                bulk_g2s_chunked(colBase + bytes0, A.cellItems, bytes1, sBar);
+            } else {
+                bulk_g2s_chunked(colBase, A.obstacles, bytes0, sBar);
+            }
+        }
+        mbar_wait(sBar, 0);
+        if (COL == COL_GRID_SMEM) {
+            sCellStart = reinterpret_cast<const int*>(colBase);
+            sItems = reinterpret_cast<const float4*>(colBase + bytes0);
+        } else {
+            sObs = reinterpret_cast<const float4*>(colBase);
+        }
+    }
+    cs.gridS = CollideGrid{sCellStart, sItems, A.cullC, A.cullInvX, A.cullInvY};
+    cs.gridG = CollideGrid{A.cellStart, A.cellItems, A.cullC, A.cullInvX, A.cullInvY};
+    cs.allS = CollideSmemAll{sObs, A.K};
+    cs.allG = CollideSmemAll{A.obstacles, A.K};
+    return cs;
+}
+
 template <int COL, bool RECORD, class Group>
-__device__ void run_plan(const KArgs& A, int maxIters, Group& grp, unsigned char* smem_raw) {
-    __shared__ __align__(8) uint64_t sBar;
+__device__ void run_plan(const KArgs& A, int maxIters, Group& grp, const ColSet& cs) {
     __shared__ int sRed[WARPS];
     __shared__ float sP[1024];
     __shared__ DevState S;
@@ -428,44 +474,13 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, unsigned char
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     DevState* st = A.st;
-
-    /* shared-memory carve-up: [R1 histograms][collision data] */
-    int* hV = reinterpret_cast<int*>(smem_raw);
-    int* hI = hV + (A.useHist ? A.c1 : 0);
-    unsigned char* colBase = smem_raw + (A.useHist ? ((2 * A.c1 * 4 + 15) & ~15) : 0);
-
-    /* stage the collision structure once per launch (bulk async copy, mbarrier completion) */
-    const float4* sObs = nullptr; const int* sCellStart = nullptr; const float4* sItems = nullptr;
-    if (COL == COL_GRID_SMEM || COL == COL_BRUTE_SMEM) {
-        uint32_t bytes0 = 0, bytes1 = 0;
-        if (COL == COL_GRID_SMEM) { bytes0 = (uint32_t)A.cellStartInts * 4u; bytes1 = (uint32_t)A.numItems * 16u; }
-        else                      { bytes0 = (uint32_t)A.K * 16u; }
-        if (tid == 0) { mbar_init(&sBar, 1); mbar_fence_init(); }
-        __syncthreads();
-        if (tid == 0) {
-            mbar_expect_tx(&sBar, bytes0 + bytes1);
-            if (COL == COL_GRID_SMEM) {
-                bulk_g2s_chunked(colBase, A.cellStart, bytes0, &sBar);
-                bulk_g2s_chunked(colBase + bytes0, A.cellItems, bytes1, &sBar);
-            } else {
-                bulk_g2s_chunked(colBase, A.obstacles, bytes0, &sBar);
-            }
-        }
-        mbar_wait(&sBar, 0);
-        if (COL == COL_GRID_SMEM) {
-            sCellStart = reinterpret_cast<const int*>(colBase);
-            sItems = reinterpret_cast<const float4*>(colBase + bytes0);
-        } else {
-            sObs = reinterpret_cast<const float4*>(colBase);
-        }
-    }
+    int* hV = cs.hV; int* hI = cs.hI;
     const DynParams dyn{A.W, A.H, A.L, A.numDisc};
-    const CollideGrid colGridS{sCellStart, sItems, A.cullC, A.cullInvX, A.cullInvY};
-    const CollideGrid colGridG{A.cellStart, A.cellItems, A.cullC, A.cullInvX, A.cullInvY};
-    const CollideSmemAll colAllS{sObs, A.K};
-    const CollideSmemAll colAllG{A.obstacles, A.K};
+    const CollideGrid& colGridS = cs.gridS; const CollideGrid& colGridG = cs.gridG;
+    const CollideSmemAll& colAllS = cs.allS; const CollideSmemAll& colAllG = cs.allG;
 
     /* every CTA keeps its own copy of the planner scalars */
+    __syncthreads();                       /* a previous call's readers of S are done */
     if (tid < COPIED_WORDS) reinterpret_cast<int*>(&S)[tid] = __ldcg(reinterpret_cast<const int*>(st) + tid);
     __syncthreads();
 
@@ -574,8 +589,114 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, unsigned char
 template <int COL, bool RECORD>
 __global__ void __launch_bounds__(TILE) expand_kernel(const KArgs A, int maxIters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t sBar;
     GridGroup grp;
-    run_plan<COL, RECORD, GridGroup>(A, maxIters, grp, smem_raw);
+    const ColSet cs = stage_collision<COL>(A, smem_raw, &sBar);
+    run_plan<COL, RECORD, GridGroup>(A, maxIters, grp, cs);
+}
+
+/* ------------------------------------------------------- batched planning (config 4) ----
+ * Many independent queries on one map: a thread-block CLUSTER (1, 2, 4 or 8 CTAs, hardware barrier) plans one
+ * query at a time in its own workspace and pulls the next query from a ticket.  Same run_plan, same results as
+ * kgmt_plan on the same (init, goal, seed). */
+struct ClusterGroup {
+    int rank, size;
+    __device__ ClusterGroup() {
+        cg::cluster_group c = cg::this_cluster();
+        rank = (int)c.block_rank(); size = (int)c.num_blocks();
+    }
+    __device__ __forceinline__ void sync() {
+        if (size == 1) __syncthreads(); else cg::this_cluster().sync();
+    }
+};
+
+struct BatchArgs {
+    KArgs base;                   /* map, parameters; the per-query pointers below override its arrays */
+    int Q, numWorkspaces;
+    const float4* initState; const float4* initCtrl; const float2* goalXY; const uint32_t* seeds;   /* [Q] */
+    DevState* states;             /* [Q] results */
+    float* paths; int* pathLen; int maxPath;                     /* [Q][maxPath][7], [Q]; null = no paths */
+    int* queryTicket; int* wsQuery;                              /* [1], [numWorkspaces] */
+    /* workspace strides (elements) */
+    size_t treeStride, mapIntsStride, chunkStride, blockStride, stageStride;
+    int* mapSlab;                 /* [ws][mapIntsStride]: R1,R1Valid,R1Invalid,R1Avail,R1Cov,R1Score x2 | R2,R2Valid,R2Invalid,R2Stamp */
+    size_t c2;
+};
+
+__device__ void begin_block(const KArgs& A, float4 rootState, float4 rootCtrl, float* sP);
+
+template <int COL>
+__global__ void __launch_bounds__(TILE) batch_kernel(const BatchArgs B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t sBar;
+    __shared__ float sPb[1024];
+    ClusterGroup grp;
+    const int tid = threadIdx.x;
+    const int ws = (int)blockIdx.x / grp.size;
+    const ColSet cs = stage_collision<COL>(B.base, smem_raw, &sBar);
+
+    /* this workspace's arrays */
+    KArgs A = B.base;
+    A.treeState = B.base.treeState + (size_t)ws * B.treeStride;
+    A.treeCtrl = B.base.treeCtrl + (size_t)ws * B.treeStride;
+    A.treeParent = B.base.treeParent + (size_t)ws * B.treeStride;
+    int* m = B.mapSlab + (size_t)ws * B.mapIntsStride;
+    const size_t c1 = (size_t)A.c1, c2 = B.c2;
+    A.R1 = m; m += c1; A.R1Valid = m; m += c1; A.R1Invalid = m; m += c1; A.R1Avail = m; m += c1; A.R1Cov = m; m += c1;
+    A.R1Score[0] = reinterpret_cast<float*>(m); m += c1; A.R1Score[1] = reinterpret_cast<float*>(m); m += c1;
+    A.R2 = m; m += c2; A.R2Valid = m; m += c2; A.R2Invalid = m; m += c2; A.R2Stamp = reinterpret_cast<unsigned*>(m);
+    A.chunkMask = B.base.chunkMask + (size_t)ws * B.chunkStride;
+    A.blockSum = B.base.blockSum + (size_t)ws * B.blockStride;
+    A.ticket = B.base.ticket + (size_t)ws * 4;
+    A.stageState = B.base.stageState + (size_t)ws * B.stageStride;
+    A.stageCtrl = B.base.stageCtrl + (size_t)ws * B.stageStride;
+    A.totalWarps = grp.size * WARPS;
+    A.iterLog = nullptr;
+
+    const int nThreads = grp.size * TILE, gtid = grp.rank * TILE + tid;
+    for (;;) {
+        if (grp.rank == 0 && tid == 0) B.wsQuery[ws] = atomicAdd(B.queryTicket, 1);
+        __threadfence();
+        grp.sync();
+        const int q = __ldcg(&B.wsQuery[ws]);
+        if (q >= B.Q) break;
+        A.st = B.states + q;
+        A.goalX = B.goalXY[q].x; A.goalY = B.goalXY[q].y; A.seed = B.seeds[q];
+        /* reset the workspace: maps and scan block sums (tree rows and staging are overwritten as they are used) */
+        {
+            int4* z = reinterpret_cast<int4*>(B.mapSlab + (size_t)ws * B.mapIntsStride);
+            const size_t n4 = B.mapIntsStride / 4;
+            for (size_t i = gtid; i < n4; i += nThreads) z[i] = make_int4(0, 0, 0, 0);
+            for (size_t i = gtid; i < B.blockStride; i += nThreads) A.blockSum[i] = 0;
+        }
+        __threadfence();
+        grp.sync();
+        if (grp.rank == 0) begin_block(A, B.initState[q], B.initCtrl[q], sPb);
+        __threadfence();
+        grp.sync();
+        run_plan<COL, false, ClusterGroup>(A, 0x7fffffff, grp, cs);
+        __threadfence();
+        grp.sync();                             /* every insertion of the last iteration has landed */
+        if (B.paths && grp.rank == 0 && tid == 0) {
+            /* solution back-trace, root first */
+            const DevState* r = A.st;
+            int len = 0;
+            const int goalIdx = *(volatile const int*)&r->goalIdx;
+            if (*(volatile const int*)&r->stop == STOP_SOLVED && goalIdx >= 0) {
+                for (int v = goalIdx; v >= 0 && len <= A.maxTree; v = __ldcg(&A.treeParent[v])) ++len;
+                int at = len - 1;
+                for (int v = goalIdx; v >= 0 && at >= 0; v = __ldcg(&A.treeParent[v]), --at) {
+                    if (at < B.maxPath) {
+                        const float4 x = __ldcg(&A.treeState[v]), u = __ldcg(&A.treeCtrl[v]);
+                        float* o = B.paths + ((size_t)q * B.maxPath + at) * 7;
+                        o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w; o[4] = u.x; o[5] = u.y; o[6] = u.z;
+                    }
+                }
+            }
+            B.pathLen[q] = len;
+        }
+        grp.sync();                             /* the workspace may be recycled */
+    }
 }
 
 /* -------------------------------------------- stages 2-4 alone (parity / sweeps) -------
@@ -640,9 +761,8 @@ __global__ void __launch_bounds__(TILE) propagate_only_kernel(const KArgs A, con
 }
 
 /* ------------------------------------------------------------------ setup kernels ------ */
-/* root insertion, KGMT.cu:85-114, then the first iteration's shape and scores */
-__global__ void __launch_bounds__(TILE) begin_kernel(const KArgs A, float4 rootState, float4 rootCtrl) {
-    __shared__ float sP[1024];
+/* root insertion, KGMT.cu:85-114, then the first iteration's shape and scores (one CTA) */
+__device__ void begin_block(const KArgs& A, float4 rootState, float4 rootCtrl, float* sP) {
     DevState* st = A.st;
     if (threadIdx.x == 0) {
         A.treeState[0] = rootState;                                                /* :85 */
@@ -652,24 +772,30 @@ __global__ void __launch_bounds__(TILE) begin_kernel(const KArgs A, float4 rootS
         const int r2 = region_r2(rootState.x, rootState.y, r1, A.R1Size, A.N, A.R2Size, A.n);   /* :89 */
         if (r1 >= 0) { A.R1[r1] = 1; A.R1Avail[r1] = 1; A.R1Valid[r1] = 1; }       /* :94,95,97 */
         if (r2 >= 0 && A.R2Stamp[r2] == 0u) { A.R2Stamp[r2] = 1u; A.R1Cov[r1] += 1; }  /* :96 */
-        st->treeSize = 1; st->frontierStart = 0; st->frontierCount = 1; st->itr = 1;
-        st->goalIdx = -1; st->goalSlot = -1; st->costToGoal = 0.0f; st->goalBest = ~0ull;
-        st->expansions = 0; st->iterationsDone = 0; st->blocksTotal = 0; st->insertDone = 0;
-        st->lastMode = st->lastChildren = st->lastFrontier = st->lastM = st->lastAccepted = st->lastItr = 0;
+        DevState z{};
+        z.treeSize = 1; z.frontierStart = 0; z.frontierCount = 1; z.itr = 1;
+        z.goalIdx = -1; z.goalSlot = -1; z.costToGoal = 0.0f; z.goalBest = ~0ull;
+        z.forceChildren = st->forceChildren;
         A.ticket[0] = A.ticket[1] = A.ticket[2] = (unsigned)A.totalWarps;
         int stop = STOP_RUNNING;
         if (A.numIterations <= 0) stop = STOP_ITER_LIMIT;
         else if (1 >= A.maxTree) stop = STOP_TREE_FULL;
-        st->stop = stop;
+        z.stop = stop;
         int mode = 0, children = 1, M = 0;
-        if (stop == STOP_RUNNING) expansion_shape(1, 1, A.maxTree, st->forceChildren, mode, children, M);
-        st->mode = mode; st->children = children; st->M = M; st->numChunks = (M + CHUNK - 1) / CHUNK;
+        if (stop == STOP_RUNNING) expansion_shape(1, 1, A.maxTree, z.forceChildren, mode, children, M);
+        z.mode = mode; z.children = children; z.M = M; z.numChunks = (M + CHUNK - 1) / CHUNK;
+        *st = z;
     }
     __syncthreads();
     scores_block(A, sP, A.R1Score[1]);              /* iteration 1 reads buffer 1 & 1 */
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) st_release_s32(&st->scoreReady, 1);
+}
+
+__global__ void __launch_bounds__(TILE) begin_kernel(const KArgs A, float4 rootState, float4 rootCtrl) {
+    __shared__ float sP[1024];
+    begin_block(A, rootState, rootCtrl, sP);
 }
 
 /* kgmt_seed_frontier: `count` nodes already copied into tree[0,count); all are frontier */

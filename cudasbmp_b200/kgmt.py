@@ -35,7 +35,7 @@ _DTYPE = {ARR_SAMPLES: (np.float32, 7), ARR_UNEXPLORED: (np.float32, 7), ARR_PAR
 ABI_SYMBOLS = [
     "kgmt_abi_version", "kgmt_default_params", "kgmt_create", "kgmt_destroy", "kgmt_last_error", "kgmt_reset", "kgmt_set_seed",
     "kgmt_set_obstacles", "kgmt_set_obstacles_host", "kgmt_plan", "kgmt_begin", "kgmt_expand_iteration", "kgmt_expand_iterations",
-    "kgmt_get_result", "kgmt_extract_path", "kgmt_stage_scores", "kgmt_stage_propagate", "kgmt_seed_frontier",
+    "kgmt_get_result", "kgmt_extract_path", "kgmt_plan_batch", "kgmt_stage_scores", "kgmt_stage_propagate", "kgmt_seed_frontier",
     "kgmt_set_children", "kgmt_checkpoint", "kgmt_restore", "kgmt_export", "kgmt_import", "kgmt_array_bytes",
     "kgmt_dump_csv", "kgmt_tree_size", "kgmt_cost_to_goal", "kgmt_r1_size", "kgmt_r2_size", "kgmt_stream",
     "kgmt_launch_count", "kgmt_get_config", "kgmt_iteration_log",
@@ -103,6 +103,8 @@ def load():
     L.kgmt_expand_iterations.argtypes = [vp, C.c_int, C.POINTER(IterStats)]
     L.kgmt_get_result.argtypes = [vp, C.POINTER(Result)]
     L.kgmt_extract_path.argtypes = [vp, C.c_int, f32p, C.c_int]
+    L.kgmt_plan_batch.argtypes = [vp, f32p, f32p, C.POINTER(C.c_uint32), C.c_int, C.c_int, C.POINTER(Result), f32p, C.c_int,
+                                  C.POINTER(C.c_int), f32p]
     L.kgmt_stage_scores.argtypes = [vp]
     L.kgmt_stage_propagate.argtypes = [vp, f32p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, f32p]
     L.kgmt_seed_frontier.argtypes = [vp, f32p, C.c_int, f32p]
@@ -216,6 +218,26 @@ class KGMT:
         self._ck(load().kgmt_plan(self._h, i.ctypes.data_as(f32p), g.ctypes.data_as(f32p), C.byref(r)))
         self.treeSize_, self.costToGoal_ = r.tree_size, r.cost_to_goal
         return r.as_dict()
+
+    def plan_batch(self, inits, goals, seeds, cluster_size=4, max_path=0):
+        """Q independent queries on this planner's map in one launch (kgmt_plan_batch).
+        Returns (results: list of dict, device_ms, paths: list of np [L,7] or None, workspaces)."""
+        a = _f32(inits).reshape(-1, 7)
+        g = _f32(goals).reshape(-1, 7)
+        sd = np.ascontiguousarray(seeds, dtype=np.uint32)
+        Q = a.shape[0]
+        res = (Result * Q)()
+        ms = C.c_float()
+        f32p = C.POINTER(C.c_float)
+        paths = np.zeros((Q, max_path, 7), dtype=np.float32) if max_path else None
+        plen = np.zeros(Q, dtype=np.int32) if max_path else None
+        ws = self._ck(load().kgmt_plan_batch(
+            self._h, a.ctypes.data_as(f32p), g.ctypes.data_as(f32p), sd.ctypes.data_as(C.POINTER(C.c_uint32)), Q,
+            int(cluster_size), res, paths.ctypes.data_as(f32p) if max_path else None, int(max_path),
+            plen.ctypes.data_as(C.POINTER(C.c_int)) if max_path else None, C.byref(ms)))
+        out = [r.as_dict() for r in res]
+        pl = [paths[q, :min(plen[q], max_path)].copy() for q in range(Q)] if max_path else None
+        return out, ms.value, pl, ws
 
     # ------------------------------------------------------------------ stepwise
     def begin(self, initial, goal):

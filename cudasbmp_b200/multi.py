@@ -31,20 +31,27 @@ def _device_for(group):
     return torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
 
 
-def plan_batch(planner, inits, goals, seeds, group=None):
+def plan_batch(planner, inits, goals, seeds, group=None, batched=True, cluster_size=2):
     """Shard Q queries over the ranks; every rank returns the full [Q, 8] float64 result table (RESULT_COLS).
 
-    planner: an object with set_seed(s) and plan(init7, goal7) -> dict (cudasbmp_b200.KGMT).  Obstacles are already set.
+    planner: cudasbmp_b200.KGMT with the obstacles already set.  batched=True plans the rank's shard in one launch
+    (kgmt_plan_batch); batched=False calls plan() once per query.  Either way every query's result is the same.
     """
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     Q = len(seeds)
     lo, hi = shard_range(Q, rank, world)
     rows = np.zeros((Q, len(RESULT_COLS)), dtype=np.float64)
-    for q in range(lo, hi):
-        planner.set_seed(int(seeds[q]))
-        r = planner.plan(inits[q], goals[q])
-        rows[q] = (q, rank, r["stop"], r["iterations"], r["tree_size"], r["cost_to_goal"], r["expansions"], r["device_ms"])
+    if hi > lo and batched and hasattr(planner, "plan_batch"):
+        # the rank's whole shard in ONE launch: thread-block clusters plan one query each (kgmt_plan_batch)
+        res, ms, _, _ = planner.plan_batch(inits[lo:hi], goals[lo:hi], np.asarray(seeds[lo:hi]), cluster_size=cluster_size)
+        for i, r in enumerate(res):
+            rows[lo + i] = (lo + i, rank, r["stop"], r["iterations"], r["tree_size"], r["cost_to_goal"], r["expansions"], ms)
+    else:
+        for q in range(lo, hi):
+            planner.set_seed(int(seeds[q]))
+            r = planner.plan(inits[q], goals[q])
+            rows[q] = (q, rank, r["stop"], r["iterations"], r["tree_size"], r["cost_to_goal"], r["expansions"], r["device_ms"])
     if world == 1:
         return rows
     # disjoint shards: a SUM all-reduce of the zero-padded table is the gather (one collective, Q x 64 bytes)

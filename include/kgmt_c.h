@@ -151,6 +151,15 @@ int  kgmt_get_result(kgmt_ctx* ctx, kgmt_result* out);
  * root first.  Returns the path length (may exceed max_rows; only max_rows are written). */
 int  kgmt_extract_path(kgmt_ctx* ctx, int node, float* h_rows7, int max_rows);
 
+/* ---- batched planning (BASELINE config 4) ----------------------------------------------------------------------
+ * Q independent queries (HOST rows of 7 floats; seed per query) on the context's map and parameters in ONE launch: a
+ * thread-block cluster of cluster_size CTAs (1, 2, 4 or 8) plans one query at a time and pulls the next from a ticket.
+ * Each query gives exactly the result kgmt_plan gives for the same (init, goal, seed).  out[Q]; h_paths7 (optional)
+ * receives [Q][max_path][7] solution rows, root first, h_path_len[Q] their lengths.  Returns the number of
+ * concurrent workspaces used (> 0) or a negative status. */
+int  kgmt_plan_batch(kgmt_ctx* ctx, const float* h_inits7, const float* h_goals7, const uint32_t* h_seeds, int Q,
+                     int cluster_size, kgmt_result* out, float* h_paths7, int max_path, int* h_path_len, float* device_ms);
+
 /* ---- stage-level entry points (parity tests, throughput sweeps) ----------------------------- */
 /* Stage 1: R1 scores from the current maps (updateR1, KGMT.cu:487-538). */
 int  kgmt_stage_scores(kgmt_ctx* ctx);

@@ -24,7 +24,7 @@ torch.cuda.synchronize()
 if world > 1: dist.barrier()
 dt = time.perf_counter() - t0
 solved = table[:, 2] == 1
-res = dict(mode="batch", gpus=world, queries=Q, wall_s=dt, queries_per_s=Q / dt, expansions_per_s=table[:, 6].sum() / dt,
+res = dict(mode="batch (one launch per rank)", gpus=world, queries=Q, wall_s=dt, queries_per_s=Q / dt, expansions_per_s=table[:, 6].sum() / dt,
            solved=int(solved.sum()), device_ms_median=float(np.median(table[:, 7])), device_ms_p95=float(np.percentile(table[:, 7], 95)),
            stops={int(k): int((table[:, 2] == k).sum()) for k in np.unique(table[:, 2])})
 if rank == 0: print(json.dumps(res))

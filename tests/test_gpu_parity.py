@@ -322,3 +322,30 @@ def test_csv_dump_matches_reference_format(tmp_path):
     assert par[0] == -1 and (par[r["tree_size"]:] == -1).all()
     s = np.loadtxt(tmp_path / "samples.csv", delimiter=",", dtype=np.float64)
     np.testing.assert_allclose(s, plan.export(K.ARR_SAMPLES), atol=6e-11 + 0, rtol=1e-7)
+
+
+# --------------------------------------------------------------------------------- batched planning (config 4)
+@pytest.mark.parametrize("cluster", [1, 4, 8])
+def test_batch_equals_one_plan_per_query(cluster):
+    """kgmt_plan_batch (thread-block clusters, one query each) gives, for every query, exactly what kgmt_plan gives
+    for the same (init, goal, seed): stop reason, iterations, tree size, cost, expansions, goal index, solution path."""
+    Q = 48
+    inits, goals = w.random_queries(Q, w.C1_OBSTACLES)
+    seeds = np.arange(100, 100 + Q)
+    cfg = dict(w.C1, maxTreeSize=12000)
+    one = _plan(cfg, w.C1_OBSTACLES)
+    ref = []
+    for q in range(Q):
+        one.set_seed(int(seeds[q]))
+        r = one.plan(inits[q], goals[q])
+        ref.append((r, one.extract_path() if r["stop"] == 1 else np.zeros((0, 7), np.float32)))
+    batch = _plan(cfg, w.C1_OBSTACLES)
+    res, ms, paths, ws = batch.plan_batch(inits, goals, seeds, cluster_size=cluster, max_path=128)
+    assert ws >= 1 and ms > 0
+    for q in range(Q):
+        r, path = ref[q]
+        for k in ("stop", "iterations", "tree_size", "expansions", "goal_index"):
+            assert res[q][k] == r[k], (q, k, res[q], r)
+        assert np.float32(res[q]["cost_to_goal"]) == np.float32(r["cost_to_goal"])
+        assert paths[q].shape == path.shape and (bits(paths[q]) == bits(path)).all()
+    assert sum(r["stop"] == 1 for r, _ in ref) > Q // 2
