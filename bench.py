@@ -235,7 +235,7 @@ def main():
         d2h += 128
         if r["stop"] == 1:
             path = plan.extract_path()
-            d2h += r["tree_size"] * 4 + len(path) * 32
+            d2h += 128 + 4 + len(path) * 28          # state block + length + the AoS-7 rows
     barrier()
     e2e_s = time.perf_counter() - t1
     cfgd = plan.config()

@@ -25,7 +25,8 @@ struct kgmt_ctx {
     int device = 0, numSMs = 0, maxCand = 0, c1 = 0;
     size_t c2 = 0;
     float R1Size = 0.f, R2Size = 0.f;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      /* the stream every call launches on */
+    cudaStream_t ownStream = nullptr;   /* created by kgmt_create; `stream` unless the caller installed its own */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     /* device memory */
     float4 *treeState = nullptr, *treeCtrl = nullptr;
@@ -78,6 +79,9 @@ struct kgmt_ctx {
         size_t mapIntsStride = 0;
     } batch;
     unsigned epochBase = 0;
+    /* sharded expansion (kgmt_shard_*) */
+    int* shardPrefix = nullptr; int* shardTotal = nullptr; int* hShardTotal = nullptr;   /* [blocksCap], [1], pinned [1] */
+    int shardBlkLo = 0, shardBlkHi = 0, shardAccepted = -1, shardGrid = 0;
     DevState resetState{};
     char err[512] = {0};
 };
@@ -123,12 +127,23 @@ static prop_fn propagate_entry(int col) {
     }
 }
 
+typedef void (*shard_fn)(const KArgs, int, int);
+static shard_fn shard_entry(int col) {
+    switch (col) {
+        case COL_GRID_SMEM: return shard_expand_kernel<COL_GRID_SMEM>;
+        case COL_GRID_GLOBAL: return shard_expand_kernel<COL_GRID_GLOBAL>;
+        case COL_BRUTE_SMEM: return shard_expand_kernel<COL_BRUTE_SMEM>;
+        default: return shard_expand_kernel<COL_BRUTE_GLOBAL>;
+    }
+}
+
 static KArgs make_args(const kgmt_ctx* c) {
     KArgs A{};
     A.treeState = c->treeState; A.treeCtrl = c->treeCtrl; A.treeParent = c->treeParent;
     A.R1 = c->R1; A.R1Valid = c->R1Valid; A.R1Invalid = c->R1Invalid; A.R1Avail = c->R1Avail; A.R1Cov = c->R1Cov;
     A.R1Score[0] = c->R1Score[0]; A.R1Score[1] = c->R1Score[1];
     A.R2 = c->R2; A.R2Valid = c->R2Valid; A.R2Invalid = c->R2Invalid; A.R2Stamp = c->R2Stamp;
+    A.R2StampDelta = nullptr;
     A.candState = c->candState; A.candCtrl = c->candCtrl; A.candParent = c->candParent;
     A.candR1 = c->candR1; A.candR2 = c->candR2; A.candFlags = c->candFlags;
     A.chunkMask = c->chunkMask; A.blockSum = c->blockSum; A.ticket = c->ticket;
@@ -173,6 +188,13 @@ static int configure(kgmt_ctx* ctx) {
         occ = std::min(occ, o);
     }
     CU(cudaFuncSetAttribute((const void*)propagate_entry(col), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)colBytes));
+    {
+        const void* sf = (const void*)shard_entry(col);
+        CU(cudaFuncSetAttribute(sf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemBytes));
+        int o = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, sf, TILE, ctx->smemBytes));
+        ctx->shardGrid = std::max(o, 1) * ctx->numSMs;
+    }
     if (occ < 1) return fail(ctx, KGMT_ERR_CUDA, "expand kernel does not fit on an SM (smem %zu B)", ctx->smemBytes);
     ctx->gridLoop = occ * ctx->numSMs;
     ctx->gridMax = occ * ctx->numSMs;
@@ -382,7 +404,9 @@ void kgmt_destroy(kgmt_ctx* ctx) {
     free_batch(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+    cudaFree(ctx->shardPrefix); cudaFree(ctx->shardTotal);
+    if (ctx->hShardTotal) cudaFreeHost(ctx->hShardTotal);
     delete ctx;
 }
 
@@ -409,7 +433,8 @@ int kgmt_create(const kgmt_params* p, kgmt_ctx** out) {
     if (prop.major < 10) return fail(ctx, KGMT_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only",
                                      prop.name, prop.major, prop.minor);
     ctx->numSMs = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking));
+    ctx->stream = ctx->ownStream;
     CU(cudaEventCreate(&ctx->ev0));
     CU(cudaEventCreate(&ctx->ev1));
 
@@ -657,6 +682,118 @@ int kgmt_plan_batch(kgmt_ctx* ctx, const float* h_inits7, const float* h_goals7,
             out[q].device_ms = ms; out[q].kernel_launches = 1;
         }
     return numWs;
+}
+
+/* ---- caller-owned stream ---------------------------------------------------------------------------------------- */
+int kgmt_set_stream(kgmt_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return KGMT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->ownStream;
+    return KGMT_OK;
+}
+
+/* ---- sharded expansion: one iteration's candidates split over `world` ranks (BASELINE config 5) ----------------- */
+size_t kgmt_shard_delta_ints(const kgmt_ctx* ctx) { return ctx ? 4 * (size_t)ctx->c1 + 4 * ctx->c2 : 0; }
+
+static KArgs make_shard_args(const kgmt_ctx* ctx, int* d_delta) {
+    KArgs A = make_args(ctx);
+    const size_t c1 = (size_t)ctx->c1, c2 = ctx->c2;
+    A.R1 = d_delta; A.R1Valid = d_delta + c1; A.R1Invalid = d_delta + 2 * c1; A.R1Avail = d_delta + 3 * c1;
+    int* d2 = d_delta + 4 * c1;
+    A.R2 = d2; A.R2Valid = d2 + c2; A.R2Invalid = d2 + 2 * c2; A.R2StampDelta = d2 + 3 * c2;
+    return A;                        /* R2Stamp, R1Cov, R1Score stay the real (replicated) arrays: read-only here */
+}
+
+int kgmt_shard_expand(kgmt_ctx* ctx, int rank, int world, int* d_delta, kgmt_shard_info* out) {
+    if (!ctx || !d_delta || world < 1 || world > 16 || rank < 0 || rank >= world) return fail(ctx, KGMT_ERR_INVALID, "bad shard arguments");
+    if (!ctx->begun) return fail(ctx, KGMT_ERR_STATE, "kgmt_shard_expand before kgmt_begin / kgmt_seed_frontier");
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->shardPrefix) {
+        CU(cudaMalloc(&ctx->shardPrefix, ctx->blocksCap * 4));
+        CU(cudaMalloc(&ctx->shardTotal, 4));
+        CU(cudaHostAlloc(&ctx->hShardTotal, 4, cudaHostAllocDefault));
+    }
+    const DevState& s = *ctx->hState;              /* as fetched by begin / the previous commit */
+    const int numBlocks = (s.numChunks + BLK_CHUNKS - 1) / BLK_CHUNKS;
+    /* contiguous, balanced ranges of 8192-candidate scan blocks: global slot order == rank-major order */
+    const int base = numBlocks / world, rem = numBlocks % world;
+    const int bLo = rank * base + std::min(rank, rem), bHi = bLo + base + (rank < rem ? 1 : 0);
+    ctx->shardBlkLo = bLo; ctx->shardBlkHi = bHi; ctx->shardAccepted = 0;
+    const int cLo = bLo * BLK_CHUNKS, cHi = std::min(bHi * BLK_CHUNKS, s.numChunks);
+    if (s.stop == STOP_RUNNING) {
+        const KArgs A = make_shard_args(ctx, d_delta);
+        const int chunks = std::max(cHi - cLo, 0);
+        const int grid = std::max(1, std::min(ctx->shardGrid, (chunks + WARPS - 1) / WARPS));
+        shard_reset_kernel<<<32, 256, 0, ctx->stream>>>(A, grid * WARPS);
+        if (chunks > 0) shard_entry(ctx->col)<<<grid, TILE, ctx->smemBytes, ctx->stream>>>(A, cLo, cHi);
+        shard_prefix_kernel<<<1, TILE, 0, ctx->stream>>>(A, bLo, bHi, ctx->shardPrefix, ctx->shardTotal);
+        CU(cudaGetLastError());
+        ctx->launches += chunks > 0 ? 3 : 2;
+        CU(cudaMemcpyAsync(ctx->hShardTotal, ctx->shardTotal, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->shardAccepted = *ctx->hShardTotal;
+    }
+    if (out) {
+        out->iteration = s.itr; out->candidates = s.M; out->children = s.children; out->frontier = s.frontierCount;
+        out->chunk_lo = cLo; out->chunk_hi = std::max(cHi, cLo); out->accepted_local = ctx->shardAccepted; out->stop = s.stop;
+    }
+    return KGMT_OK;
+}
+
+int kgmt_shard_pack(kgmt_ctx* ctx, void* d_send, int cap_rows) {
+    if (!ctx || !d_send || cap_rows < 4 || (cap_rows & 3)) return fail(ctx, KGMT_ERR_INVALID, "cap_rows must be a positive multiple of 4");
+    if (ctx->shardAccepted < 0) return fail(ctx, KGMT_ERR_STATE, "kgmt_shard_pack before kgmt_shard_expand");
+    if (ctx->shardAccepted > cap_rows) return fail(ctx, KGMT_ERR_INVALID, "cap_rows %d < accepted rows %d", cap_rows, ctx->shardAccepted);
+    CU(cudaSetDevice(ctx->device));
+    const int nb = ctx->shardBlkHi - ctx->shardBlkLo;
+    if (nb > 0 && ctx->shardAccepted > 0) {
+        const KArgs A = make_args(ctx);
+        unsigned char* b = (unsigned char*)d_send;
+        shard_pack_kernel<<<std::min(nb, ctx->numSMs * 8), TILE, 0, ctx->stream>>>(
+            A, ctx->shardBlkLo, ctx->shardBlkHi, ctx->shardPrefix, (float4*)b, (float4*)(b + (size_t)cap_rows * 16),
+            (int*)(b + (size_t)cap_rows * 32));
+        CU(cudaGetLastError());
+        ctx->launches += 1;
+    }
+    return KGMT_OK;
+}
+
+int kgmt_shard_commit(kgmt_ctx* ctx, const void* d_recv, int cap_rows, const int* h_counts, int world, int* d_delta,
+                      kgmt_iter_stats* out) {
+    if (!ctx || !d_recv || !h_counts || !d_delta || world < 1 || world > 16 || cap_rows < 4 || (cap_rows & 3))
+        return fail(ctx, KGMT_ERR_INVALID, "bad commit arguments");
+    if (ctx->shardAccepted < 0) return fail(ctx, KGMT_ERR_STATE, "kgmt_shard_commit before kgmt_shard_expand");
+    CU(cudaSetDevice(ctx->device));
+    ShardCommit C{};
+    C.recv = (const unsigned char*)d_recv; C.cap = cap_rows; C.world = world;
+    long long total = 0;
+    for (int g = 0; g < world; ++g) {
+        if (h_counts[g] < 0 || h_counts[g] > cap_rows) return fail(ctx, KGMT_ERR_INVALID, "count of rank %d out of range", g);
+        C.prefix[g] = (int)total; total += h_counts[g];
+    }
+    C.prefix[world] = (int)total;
+    if (total > (long long)ctx->p.max_tree_size - ctx->hState->treeSize)
+        return fail(ctx, KGMT_ERR_INVALID, "%lld accepted rows do not fit the tree", total);
+    if (ctx->hState->stop == STOP_RUNNING) {
+        const KArgs A = make_args(ctx);
+        if (total > 0)
+            shard_insert_kernel<<<(int)std::min<long long>((total + TILE - 1) / TILE, (long long)ctx->numSMs * 8), TILE, 0, ctx->stream>>>(A, C);
+        shard_apply_kernel<<<(unsigned)std::min<size_t>((ctx->c2 + 255) / 256, (size_t)ctx->numSMs * 8), 256, 0, ctx->stream>>>(A, d_delta, ctx->c2);
+        shard_finalize_kernel<<<1, TILE, 0, ctx->stream>>>(A, C);
+        CU(cudaGetLastError());
+        ctx->launches += total > 0 ? 3 : 2;
+    }
+    ctx->shardAccepted = -1;
+    int rc = fetch_state(ctx);
+    if (rc) return rc;
+    if (out) {
+        const DevState& s = *ctx->hState;
+        out->iteration = s.lastItr; out->mode = s.lastMode; out->children = s.lastChildren; out->frontier = s.lastFrontier;
+        out->candidates = s.lastM; out->accepted = s.lastAccepted; out->tree_size = s.treeSize; out->stop = s.stop;
+        out->cost_to_goal = s.costToGoal; out->goal_index = s.goalIdx;
+    }
+    return KGMT_OK;
 }
 
 /* ---- stage-level entry points ------------------------------------------------------------- */
@@ -908,20 +1045,21 @@ int kgmt_extract_path(kgmt_ctx* ctx, int node, float* h_rows7, int max_rows) {
     const int T = ctx->hState->treeSize;
     if (node < 0) node = ctx->hState->goalIdx;
     if (node < 0 || node >= T) return fail(ctx, KGMT_ERR_INVALID, "no such node %d (tree size %d)", node, T);
-    std::vector<int> parent((size_t)T);
-    CU(cudaMemcpyAsync(parent.data(), ctx->treeParent, (size_t)T * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    /* back-trace on the device (one thread walks the parent links, L2-resident), one D2H of the rows it found */
+    const size_t rowsCap = (size_t)std::max(max_rows, 0);
+    rc = ensure_scratch(ctx, 16 + rowsCap * 28);
+    if (rc) return rc;
+    const KArgs A = make_args(ctx);
+    trace_path_kernel<<<1, 32, 0, ctx->stream>>>(A, node, T, (int*)ctx->scratch, (float*)((char*)ctx->scratch + 16), max_rows);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    int len = 0;
+    CU(cudaMemcpyAsync(&len, ctx->scratch, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    std::vector<int> chain;
-    for (int v = node; v >= 0 && (int)chain.size() <= T; v = parent[v]) chain.push_back(v);
-    std::reverse(chain.begin(), chain.end());
-    const int len = (int)chain.size();
-    for (int i = 0; i < len && i < max_rows; ++i) {
-        float4 s, c;
-        CU(cudaMemcpyAsync(&s, ctx->treeState + chain[i], 16, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(&c, ctx->treeCtrl + chain[i], 16, cudaMemcpyDeviceToHost, ctx->stream));
+    const int rows = std::min(len, max_rows);
+    if (rows > 0) {
+        CU(cudaMemcpyAsync(h_rows7, (char*)ctx->scratch + 16, (size_t)rows * 28, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        float* r = h_rows7 + (size_t)i * 7;
-        r[0] = s.x; r[1] = s.y; r[2] = s.z; r[3] = s.w; r[4] = c.x; r[5] = c.y; r[6] = c.z;
     }
     return len;
 }

@@ -66,7 +66,9 @@ struct DevState {
     int pad1;
 };
 constexpr int COPIED_WORDS = 24;
+constexpr int THRESHOLD_WORD = 7;         /* R1Threshold: written by scores_block straight to global memory, never copied back */
 static_assert(offsetof(DevState, goalBest) == COPIED_WORDS * 4, "DevState layout");
+static_assert(offsetof(DevState, R1Threshold) == THRESHOLD_WORD * 4, "DevState layout");
 
 struct KArgs {
     /* tree, SoA */
@@ -76,6 +78,7 @@ struct KArgs {
     /* occupancy maps */
     int *R1, *R1Valid, *R1Invalid, *R1Avail, *R1Cov; float* R1Score[2];   /* scores: buffer itr&1 */
     int *R2, *R2Valid, *R2Invalid; unsigned* R2Stamp;
+    int* R2StampDelta;            /* sharded expansion only: cells this rank reached for the first time (0/1) */
     /* per-candidate records (null unless recording) */
     float4* candState; float4* candCtrl; int* candParent; int* candR1; int* candR2; unsigned char* candFlags;
     /* ordered insertion: everything indexed by iteration parity / iteration mod 3 */
@@ -284,7 +287,7 @@ __device__ __forceinline__ IterView make_view(const KArgs& A, const DevState& S)
 /* ---------------------------------------------------------------- phase A: one chunk ---
  * 32 candidates, one per lane: stages 2-5a.  No communication outside the warp.
  * scoresOk (warp-uniform) remembers that this iteration's score buffer has been seen complete. */
-template <class Collide, bool RECORD>
+template <class Collide, bool RECORD, bool SHARD = false>
 __device__ __forceinline__ void expand_chunk(const KArgs& A, const IterView& it, const DynParams& dyn,
                                              const Collide& col, int c, int lane, int* hV, int* hI, bool& scoresOk) {
     const int s = c * CHUNK + lane;
@@ -314,7 +317,8 @@ __device__ __forceinline__ void expand_chunk(const KArgs& A, const IterView& it,
                 const unsigned stamp = __ldcg(&A.R2Stamp[r2]);
                 if (stamp == 0u || stamp > (unsigned)it.itr) accept = true;        /* unavailable at iteration start */
                 if (stamp == 0u) {
-                    if (atomicCAS(&A.R2Stamp[r2], 0u, (unsigned)it.itr + 1u) == 0u) atomicAdd(&A.R1Cov[r1], 1);
+                    if (SHARD) A.R2StampDelta[r2] = 1;      /* the stamp itself is set at commit, after the all-reduce */
+                    else if (atomicCAS(&A.R2Stamp[r2], 0u, (unsigned)it.itr + 1u) == 0u) atomicAdd(&A.R1Cov[r1], 1);
                 }
                 atomicAdd(&A.R2Valid[r2], 1);
             }
@@ -337,7 +341,7 @@ __device__ __forceinline__ void expand_chunk(const KArgs& A, const IterView& it,
         const float cost = __fadd_rn(parentCost, u.duration);                      /* :585-586, :631-633 */
         __stcg(&it.stageState[at], x);
         __stcg(&it.stageCtrl[at], make_float4(u.a, u.steering, u.duration, cost));
-        if (in_goal(x.x, x.y, A.goalX, A.goalY, A.goalR))                          /* :589; min cost, then first in order */
+        if (!SHARD && in_goal(x.x, x.y, A.goalX, A.goalY, A.goalR))               /* :589; min cost, then first in order */
             atomicMin(&A.st->goalBest, ((unsigned long long)__float_as_uint(cost) << 32) | (unsigned)s);
     }
     if (lane == 0) {
@@ -572,7 +576,7 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, const ColSet&
             for (int b = tid; b < A.blocksCap; b += TILE) A.blockSum[(size_t)r * A.blocksCap + b] = 0;
             if (tid == 0) A.ticket[r] = (unsigned)totalWarps;
         }
-        if (grp.rank == 0 && tid < COPIED_WORDS)            /* for the host and for the next launch */
+        if (grp.rank == 0 && tid < COPIED_WORDS && tid != THRESHOLD_WORD)   /* for the host and for the next launch */
             reinterpret_cast<int*>(st)[tid] = reinterpret_cast<const int*>(&S)[tid];
 
         /* ---- phase B: ordered insertion, scan blocks strided over the CTAs */
@@ -697,6 +701,225 @@ __global__ void __launch_bounds__(TILE) batch_kernel(const BatchArgs B) {
         }
         grp.sync();                             /* the workspace may be recycled */
     }
+}
+
+/* ------------------------------------------ sharded expansion (config 5) ----
+ * The candidates of ONE iteration are split over G ranks (tree and maps replicated on every GPU):
+ *   shard_expand   rank g runs stages 2-5a on its contiguous chunk range; counter increments go to a zeroed DELTA slab
+ *                  (A.R1.., A.R2.. point into it), first-reached R2 cells are flagged in R2StampDelta; accepted rows are
+ *                  ballot-compacted into the staging buffers exactly as in the single-GPU kernel
+ *   shard_prefix   exclusive prefix of the rank's scan-block sums + its accepted count
+ *   shard_pack     accepted rows, in candidate order, into the send buffer [state f4[cap] | ctrl f4[cap] | slot i32[cap]]
+ *   -- NCCL: all-gather(counts), all-gather(rows), all-reduce SUM(delta slab) --
+ *   shard_insert   every rank inserts all rows in rank-major (= global candidate) order: the tree, parent links and
+ *                  costs are bit-identical to the single-GPU result
+ *   shard_apply    maps += reduced deltas, stamps, R1Cov, R1Avail; the slab is zeroed for the next iteration
+ *   shard_finalize goal node, planner scalars (advance_state), next iteration's scores */
+__global__ void shard_reset_kernel(const KArgs A, int totalWarps) {
+    const DevState* st = A.st;
+    int* bs = A.blockSum + (size_t)(st->itr % 3) * A.blocksCap;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < A.blocksCap; b += gridDim.x * blockDim.x) bs[b] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) A.ticket[3] = (unsigned)totalWarps;
+}
+
+template <int COL>
+__global__ void __launch_bounds__(TILE) shard_expand_kernel(const KArgs A, int chunkLo, int chunkHi) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t sBar;
+    __shared__ DevState S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const ColSet cs = stage_collision<COL>(A, smem_raw, &sBar);
+    if (tid < COPIED_WORDS) reinterpret_cast<int*>(&S)[tid] = __ldcg(reinterpret_cast<const int*>(A.st) + tid);
+    int* hV = cs.hV; int* hI = cs.hI;
+    if (A.useHist) for (int c = tid; c < 2 * A.c1; c += TILE) hV[c] = 0;
+    __syncthreads();
+    if (S.stop != STOP_RUNNING) return;
+    const IterView it = make_view(A, S);
+    const DynParams dyn{A.W, A.H, A.L, A.numDisc};
+    bool scoresOk = true;                  /* the scores were produced by the previous commit, stream-ordered */
+    int c = chunkLo + (int)blockIdx.x * WARPS + warp;
+    int t = 0;
+    const int hi = min(chunkHi, it.numChunks);
+    while (c < hi) {
+        if (lane == 0) t = (int)atomicAdd(&A.ticket[3], 1u);
+        if (COL == COL_GRID_SMEM)        expand_chunk<CollideGrid, false, true>(A, it, dyn, cs.gridS, c, lane, hV, hI, scoresOk);
+        else if (COL == COL_GRID_GLOBAL) expand_chunk<CollideGrid, false, true>(A, it, dyn, cs.gridG, c, lane, hV, hI, scoresOk);
+        else if (COL == COL_BRUTE_SMEM)  expand_chunk<CollideSmemAll, false, true>(A, it, dyn, cs.allS, c, lane, hV, hI, scoresOk);
+        else                             expand_chunk<CollideSmemAll, false, true>(A, it, dyn, cs.allG, c, lane, hV, hI, scoresOk);
+        c = chunkLo + __shfl_sync(0xffffffffu, t, 0);
+    }
+    __syncthreads();
+    if (A.useHist) {
+        for (int r = tid; r < A.c1; r += TILE) {
+            const int v = hV[r], iv = hI[r];
+            if (v | iv) {
+                atomicAdd(&A.R1[r], v + iv);
+                if (v) atomicAdd(&A.R1Valid[r], v);
+                if (iv) atomicAdd(&A.R1Invalid[r], iv);
+            }
+        }
+    }
+}
+
+/* one CTA: prefix[b - blkLo] = accepted rows of the rank's scan blocks before b; *total = the rank's accepted count */
+__global__ void __launch_bounds__(TILE) shard_prefix_kernel(const KArgs A, int blkLo, int blkHi, int* prefix, int* total) {
+    __shared__ int sRed[WARPS];
+    __shared__ int sCarry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* bs = A.blockSum + (size_t)(A.st->itr % 3) * A.blocksCap;
+    if (tid == 0) sCarry = 0;
+    __syncthreads();
+    for (int b0 = blkLo; b0 < blkHi; b0 += TILE) {
+        const int b = b0 + tid;
+        const int v = (b < blkHi) ? __ldcg(&bs[b]) : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) sRed[warp] = incl;
+        __syncthreads();
+        int wb = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) if (w < warp) wb += sRed[w];
+        const int carry = sCarry;
+        if (b < blkHi) prefix[b - blkLo] = carry + wb + incl - v;
+        __syncthreads();
+        if (tid == TILE - 1) sCarry = carry + wb + incl;
+        __syncthreads();
+    }
+    if (tid == 0) *total = sCarry;
+}
+
+/* CTA per scan block: the block's accepted rows, in candidate order, into the send sections (same scan as insert_block) */
+__global__ void __launch_bounds__(TILE) shard_pack_kernel(const KArgs A, int blkLo, int blkHi, const int* prefix,
+                                                          float4* sendState, float4* sendCtrl, int* sendSlot) {
+    __shared__ int sScan[WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DevState* st = A.st;
+    const int itr = st->itr, numChunks = st->numChunks;
+    const unsigned* chunkMask = A.chunkMask + (size_t)(itr & 1) * A.chunksCap;
+    const float4* stageState = A.stageState + (size_t)(itr & 1) * A.maxCand;
+    const float4* stageCtrl = A.stageCtrl + (size_t)(itr & 1) * A.maxCand;
+    for (int blk = blkLo + (int)blockIdx.x; blk < blkHi; blk += (int)gridDim.x) {
+        const int c = blk * BLK_CHUNKS + tid;
+        const unsigned mask = (c < numChunks) ? __ldcg(&chunkMask[c]) : 0u;
+        const int cnt = __popc(mask);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        __syncthreads();
+        if (lane == 31) sScan[warp] = incl;
+        __syncthreads();
+        int warpBase = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) if (w < warp) warpBase += sScan[w];
+        const int W = __shfl_sync(0xffffffffu, incl, 31);
+        const int c0 = blk * BLK_CHUNKS + warp * 32;
+        const int dst0 = __ldcg(&prefix[blk - blkLo]) + warpBase;
+        for (int q0 = 0; q0 < W; q0 += 32) {
+            const int q = q0 + lane;
+            int i = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, incl, i + step - 1);
+                if (v <= q) i += step;
+            }
+            i = min(i, 31);
+            const unsigned m = __shfl_sync(0xffffffffu, mask, i);
+            const int excl = __shfl_sync(0xffffffffu, incl - cnt, i);
+            if (q < W) {
+                const int r = q - excl;
+                const int bit = (int)__fns(m, 0, r + 1);
+                const int ci = c0 + i;
+                sendState[dst0 + q] = __ldcg(&stageState[ci * CHUNK + r]);
+                sendCtrl[dst0 + q] = __ldcg(&stageCtrl[ci * CHUNK + r]);
+                sendSlot[dst0 + q] = ci * CHUNK + bit;
+            }
+        }
+    }
+}
+
+struct ShardCommit {
+    const unsigned char* recv;    /* [world] segments of cap rows: state f4[cap] | ctrl f4[cap] | slot i32[cap] */
+    int cap, world;
+    int prefix[17];               /* prefix[g] = rows of ranks < g; prefix[world] = all accepted rows */
+};
+
+__global__ void __launch_bounds__(TILE) shard_insert_kernel(const KArgs A, const ShardCommit C) {
+    const DevState* st = A.st;
+    const int treeSize = st->treeSize, frontierStart = st->frontierStart, children = st->children;
+    const int total = C.prefix[C.world];
+    const size_t segBytes = (size_t)C.cap * 36;
+    for (int q = blockIdx.x * TILE + threadIdx.x; q < total; q += gridDim.x * TILE) {
+        int g = 0;
+        while (q >= C.prefix[g + 1]) ++g;
+        const int j = q - C.prefix[g];
+        const unsigned char* seg = C.recv + (size_t)g * segBytes;
+        const float4 x = reinterpret_cast<const float4*>(seg)[j];
+        const float4 u = reinterpret_cast<const float4*>(seg + (size_t)C.cap * 16)[j];
+        const int slot = reinterpret_cast<const int*>(seg + (size_t)C.cap * 32)[j];
+        const int dst = treeSize + q;
+        A.treeState[dst] = x;                                                      /* updateG, KGMT.cu:555-591 */
+        A.treeCtrl[dst] = u;
+        A.treeParent[dst] = frontierStart + slot / children;
+        if (in_goal(x.x, x.y, A.goalX, A.goalY, A.goalR))
+            atomicMin(&A.st->goalBest, ((unsigned long long)__float_as_uint(u.w) << 32) | (unsigned)q);   /* keyed by row */
+    }
+}
+
+/* maps += all-reduced deltas (KGMT.cu:392-411 summed over the ranks); the slab is left zeroed.
+ * delta layout: R1, R1Valid, R1Invalid, (R1Avail scratch) [c1] | R2, R2Valid, R2Invalid, R2StampDelta [c2] */
+__global__ void shard_apply_kernel(const KArgs A, int* delta, size_t c2) {
+    const size_t c1 = (size_t)A.c1;
+    const unsigned stampNew = (unsigned)A.st->itr + 1u;
+    const int nn = A.n * A.n;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < c2; i += stride) {
+        int* d = delta + 4 * c1;
+        const int a = d[i], v = d[c2 + i], iv = d[2 * c2 + i], sd = d[3 * c2 + i];
+        if (a) { A.R2[i] += a; d[i] = 0; }
+        if (v) { A.R2Valid[i] += v; d[c2 + i] = 0; }
+        if (iv) { A.R2Invalid[i] += iv; d[2 * c2 + i] = 0; }
+        if (sd) {
+            if (A.R2Stamp[i] == 0u) { A.R2Stamp[i] = stampNew; atomicAdd(&A.R1Cov[i / nn], 1); }
+            d[3 * c2 + i] = 0;
+        }
+        if (i < c1) {
+            const int a1 = delta[i], v1 = delta[c1 + i], i1 = delta[2 * c1 + i];
+            if (a1) { A.R1[i] += a1; delta[i] = 0; }
+            if (v1) { A.R1Valid[i] += v1; A.R1Avail[i] = 1; delta[c1 + i] = 0; }
+            if (i1) { A.R1Invalid[i] += i1; delta[2 * c1 + i] = 0; }
+            delta[3 * c1 + i] = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TILE) shard_finalize_kernel(const KArgs A, const ShardCommit C) {
+    __shared__ float sP[1024];
+    __shared__ DevState S;
+    const int tid = threadIdx.x;
+    DevState* st = A.st;
+    if (tid < COPIED_WORDS) reinterpret_cast<int*>(&S)[tid] = __ldcg(reinterpret_cast<const int*>(st) + tid);
+    __syncthreads();
+    const int treeSize0 = S.treeSize;
+    if (tid == 0) {
+        /* shard_insert keys the goal minimum by ROW (rank-major row order == candidate order, so ties break the same
+         * way); turn it back into the (cost, candidate slot) key advance_state expects and record the tree index */
+        unsigned long long gb = *(volatile unsigned long long*)&st->goalBest;
+        if (gb != ~0ull && S.costToGoal == 0.0f) {
+            const int q = (int)(unsigned)gb;
+            int g = 0;
+            while (q >= C.prefix[g + 1]) ++g;
+            const int* slots = reinterpret_cast<const int*>(C.recv + (size_t)g * C.cap * 36 + (size_t)C.cap * 32);
+            gb = (gb & 0xffffffff00000000ull) | (unsigned)slots[q - C.prefix[g]];
+            st->goalIdx = treeSize0 + q;
+        }
+        advance_state(A, S, C.prefix[C.world], gb);
+    }
+    __syncthreads();
+    if (S.stop == STOP_RUNNING) scores_block(A, sP, A.R1Score[S.itr & 1]);
+    __syncthreads();
+    if (tid < COPIED_WORDS && tid != THRESHOLD_WORD) reinterpret_cast<int*>(st)[tid] = reinterpret_cast<const int*>(&S)[tid];
+    if (tid == 0) { st->scoreReady = S.itr; st->insertDone = S.blocksTotal; }
 }
 
 /* -------------------------------------------- stages 2-4 alone (parity / sweeps) -------
@@ -849,6 +1072,30 @@ __global__ void recount_cov_kernel(const KArgs A) {
 __global__ void __launch_bounds__(TILE) scores_kernel(const KArgs A) {
     __shared__ float sP[1024];
     scores_block(A, sP, A.R1Score[A.st->itr & 1]);
+}
+
+/* solution back-trace: walk the parent links from `node` to the root, write the chain root
+ * first as AoS-7 rows (the reference's samples layout) and its length.  Lanes walk in lock step from staggered
+ * starts: lane l first skips l links, then every lane advances 32 links per trip. */
+__global__ void trace_path_kernel(const KArgs A, int node, int treeSize, int* outLen, float* rows7, int maxRows) {
+    const int lane = threadIdx.x;
+    int len = 0;
+    if (lane == 0) {
+        for (int v = node; v >= 0 && len <= treeSize; v = __ldcg(&A.treeParent[v])) ++len;
+        *outLen = len;
+    }
+    len = __shfl_sync(0xffffffffu, len, 0);
+    /* row `at` (root = 0) is the node reached after len-1-at links; one link walk per lane, rows strided by 32 */
+    int v = node, at = len - 1;
+    for (int i = 0; i < lane && v >= 0; ++i) { v = __ldcg(&A.treeParent[v]); --at; }
+    while (v >= 0 && at >= 0) {
+        if (at < maxRows) {
+            const float4 x = __ldcg(&A.treeState[v]), u = __ldcg(&A.treeCtrl[v]);
+            float* o = rows7 + (size_t)at * 7;
+            o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w; o[4] = u.x; o[5] = u.y; o[6] = u.z;
+        }
+        for (int i = 0; i < 32 && v >= 0; ++i) { v = __ldcg(&A.treeParent[v]); --at; }
+    }
 }
 
 /* views in the reference's element layout (export) */

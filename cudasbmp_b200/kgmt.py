@@ -39,6 +39,7 @@ ABI_SYMBOLS = [
     "kgmt_set_children", "kgmt_checkpoint", "kgmt_restore", "kgmt_export", "kgmt_import", "kgmt_array_bytes",
     "kgmt_dump_csv", "kgmt_tree_size", "kgmt_cost_to_goal", "kgmt_r1_size", "kgmt_r2_size", "kgmt_stream",
     "kgmt_launch_count", "kgmt_get_config", "kgmt_iteration_log",
+    "kgmt_set_stream", "kgmt_shard_delta_ints", "kgmt_shard_expand", "kgmt_shard_pack", "kgmt_shard_commit",
 ]
 
 
@@ -58,6 +59,14 @@ class IterStats(C.Structure):
     _fields_ = [("iteration", C.c_int), ("mode", C.c_int), ("children", C.c_int), ("frontier", C.c_int),
                 ("candidates", C.c_int), ("accepted", C.c_int), ("tree_size", C.c_int), ("stop", C.c_int),
                 ("cost_to_goal", C.c_float), ("goal_index", C.c_int)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class ShardInfo(C.Structure):
+    _fields_ = [("iteration", C.c_int), ("candidates", C.c_int), ("children", C.c_int), ("frontier", C.c_int),
+                ("chunk_lo", C.c_int), ("chunk_hi", C.c_int), ("accepted_local", C.c_int), ("stop", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -129,6 +138,12 @@ def load():
     L.kgmt_launch_count.restype = C.c_longlong
     L.kgmt_get_config.argtypes = [vp, C.POINTER(C.c_int)]
     L.kgmt_iteration_log.argtypes = [vp, C.c_int, C.POINTER(C.c_ulonglong), C.c_int]
+    L.kgmt_set_stream.argtypes = [vp, vp]
+    L.kgmt_shard_delta_ints.argtypes = [vp]
+    L.kgmt_shard_delta_ints.restype = C.c_size_t
+    L.kgmt_shard_expand.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(ShardInfo)]
+    L.kgmt_shard_pack.argtypes = [vp, vp, C.c_int]
+    L.kgmt_shard_commit.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.c_int, vp, C.POINTER(IterStats)]
     _lib = L
     return L
 
@@ -299,6 +314,31 @@ class KGMT:
         buf = np.zeros((max_rows, 7), dtype=np.float32)
         n = self._ck(load().kgmt_extract_path(self._h, int(node), buf.ctypes.data_as(C.POINTER(C.c_float)), max_rows))
         return buf[:min(n, max_rows)].copy()
+
+    # ------------------------------------------------------------------ sharded expansion (config 5)
+    def set_stream(self, cuda_stream):
+        """Launch on the caller's CUDA stream (int handle, e.g. torch.cuda.current_stream().cuda_stream); 0/None = own."""
+        self._ck(load().kgmt_set_stream(self._h, C.c_void_p(int(cuda_stream)) if cuda_stream else None))
+
+    def shard_delta_ints(self):
+        return load().kgmt_shard_delta_ints(self._h)
+
+    def shard_expand(self, rank, world, delta_ptr):
+        """delta_ptr: device pointer (int) of the zeroed int32 slab of shard_delta_ints() elements."""
+        info = ShardInfo()
+        self._ck(load().kgmt_shard_expand(self._h, int(rank), int(world), C.c_void_p(int(delta_ptr)), C.byref(info)))
+        return info.as_dict()
+
+    def shard_pack(self, send_ptr, cap_rows):
+        self._ck(load().kgmt_shard_pack(self._h, C.c_void_p(int(send_ptr)), int(cap_rows)))
+
+    def shard_commit(self, recv_ptr, cap_rows, counts, delta_ptr):
+        cnt = (C.c_int * len(counts))(*[int(c) for c in counts])
+        s = IterStats()
+        self._ck(load().kgmt_shard_commit(self._h, C.c_void_p(int(recv_ptr)), int(cap_rows), cnt, len(counts),
+                                          C.c_void_p(int(delta_ptr)), C.byref(s)))
+        self.treeSize_, self.costToGoal_ = s.tree_size, s.cost_to_goal
+        return s.as_dict()
 
     # ------------------------------------------------------------------ data
     def export(self, array_id):

@@ -160,6 +160,36 @@ int  kgmt_extract_path(kgmt_ctx* ctx, int node, float* h_rows7, int max_rows);
 int  kgmt_plan_batch(kgmt_ctx* ctx, const float* h_inits7, const float* h_goals7, const uint32_t* h_seeds, int Q,
                      int cluster_size, kgmt_result* out, float* h_paths7, int max_path, int* h_path_len, float* device_ms);
 
+/* ---- sharded expansion (BASELINE config 5; SURVEY.md §8e "sharded expansion") --------------------------------------
+ * ONE iteration's candidates are split over `world` ranks; tree and maps are replicated on every GPU and stay
+ * bit-identical to a single-GPU run (the reference has no multi-GPU mode; this replaces one while-loop body,
+ * KGMT.cu:118-259, per round of the three calls below).  The collectives in between are the caller's (NCCL):
+ *
+ *   kgmt_shard_expand   stages 2-5a on this rank's contiguous candidate range; region-counter increments go to the
+ *                       zero-initialised DEVICE slab d_delta (kgmt_shard_delta_ints ints: R1,R1Valid,R1Invalid,scratch
+ *                       [N*N] | R2,R2Valid,R2Invalid,first-reached flags [N*N*n*n]); reports the rows it accepted
+ *        -> all-gather(accepted_local) ; cap_rows = max over ranks rounded up to a multiple of 4
+ *   kgmt_shard_pack     this rank's accepted rows, candidate order, into DEVICE d_send:
+ *                       float4 state[cap_rows] | float4 (a, steering, duration, cost)[cap_rows] | int32 slot[cap_rows]
+ *        -> all-gather(d_send, 36*cap_rows bytes per rank) into d_recv ; all-reduce SUM(d_delta)
+ *   kgmt_shard_commit   inserts every rank's rows in rank order (= global candidate order), adds the reduced deltas to
+ *                       the maps (the slab is zeroed again), advances the planner, scores the next iteration
+ * Mixing these with kgmt_expand_iteration(s) on the same context is allowed between complete rounds. */
+typedef struct kgmt_shard_info {
+    int iteration, candidates, children, frontier;   /* the pending iteration (identical on every rank) */
+    int chunk_lo, chunk_hi;                          /* this rank's 32-candidate chunks [lo, hi) */
+    int accepted_local;                              /* rows this rank contributes */
+    int stop;                                        /* kgmt_stop before this iteration */
+} kgmt_shard_info;
+size_t kgmt_shard_delta_ints(const kgmt_ctx* ctx);
+int  kgmt_shard_expand(kgmt_ctx* ctx, int rank, int world, int* d_delta, kgmt_shard_info* out);
+int  kgmt_shard_pack(kgmt_ctx* ctx, void* d_send, int cap_rows);
+int  kgmt_shard_commit(kgmt_ctx* ctx, const void* d_recv, int cap_rows, const int* h_counts, int world, int* d_delta,
+                       kgmt_iter_stats* out);
+/* launch on the caller's CUDA stream (cudaStream_t) instead of the context's own; NULL restores it.  Lets the calls
+ * above order with NCCL collectives enqueued on the same stream without extra synchronisation. */
+int  kgmt_set_stream(kgmt_ctx* ctx, void* cuda_stream);
+
 /* ---- stage-level entry points (parity tests, throughput sweeps) ----------------------------- */
 /* Stage 1: R1 scores from the current maps (updateR1, KGMT.cu:487-538). */
 int  kgmt_stage_scores(kgmt_ctx* ctx);

@@ -1,0 +1,120 @@
+"""Sharded expansion (config 5) on ONE GPU: `world` ranks are emulated by `world` contexts that each run
+kgmt_shard_expand / pack on their slot range; the collectives are done by hand (concatenate the send buffers, add the
+delta slabs).  Every rank's tree, parent links, costs and region maps must stay bit-identical to a single-context run of
+kgmt_expand_iteration, iteration by iteration (the sharding is invisible in the result)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from cudasbmp_b200 import kgmt as K          # noqa: E402
+from cudasbmp_b200 import workloads as w     # noqa: E402
+from cudasbmp_b200.sharded import ROW_BYTES, ShardedExpander, round_up4     # noqa: E402
+
+MAPS = (K.ARR_R1, K.ARR_R1VALID, K.ARR_R1INVALID, K.ARR_R1AVAIL, K.ARR_R1SCORE, K.ARR_R2, K.ARR_R2VALID, K.ARR_R2INVALID,
+        K.ARR_R2AVAIL)
+
+
+def _same_state(a, b, upto):
+    np.testing.assert_array_equal(a.export(K.ARR_SAMPLES)[:upto].view(np.uint32), b.export(K.ARR_SAMPLES)[:upto].view(np.uint32))
+    np.testing.assert_array_equal(a.export(K.ARR_PARENT)[:upto], b.export(K.ARR_PARENT)[:upto])
+    np.testing.assert_array_equal(a.export(K.ARR_COSTS)[:upto].view(np.uint32), b.export(K.ARR_COSTS)[:upto].view(np.uint32))
+    for m in MAPS:
+        np.testing.assert_array_equal(a.export(m).view(np.uint32), b.export(m).view(np.uint32), err_msg="map %d" % m)
+
+
+def _emulated_round(ranks, deltas, dev):
+    world = len(ranks)
+    torch.cuda.synchronize()
+    infos = [p.shard_expand(g, world, deltas[g].data_ptr()) for g, p in enumerate(ranks)]
+    counts = [i["accepted_local"] for i in infos]
+    cap = round_up4(max(counts))
+    sends = [torch.zeros(cap * ROW_BYTES, dtype=torch.uint8, device=dev) for _ in ranks]
+    for p, s in zip(ranks, sends):
+        p.shard_pack(s.data_ptr(), cap)
+    torch.cuda.synchronize()
+    recv = torch.cat(sends)                                   # the all-gather
+    total = torch.stack(deltas).sum(dim=0).to(torch.int32)    # the all-reduce
+    stats = []
+    for g, p in enumerate(ranks):
+        deltas[g].copy_(total)
+        torch.cuda.synchronize()
+        stats.append(p.shard_commit(recv.data_ptr(), cap, counts, deltas[g].data_ptr()))
+        torch.cuda.synchronize()
+        assert int(deltas[g].abs().sum()) == 0                # the slab is handed back zeroed
+    assert all(s == stats[0] for s in stats)
+    return stats[0], infos, counts
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("cfgname", ["c1", "c2small"])
+def test_sharded_iterations_equal_single_gpu(world, cfgname):
+    dev = torch.device("cuda", 0)
+    if cfgname == "c1":
+        cfg, obs, init, goal = w.C1, w.C1_OBSTACLES, w.C1_INIT, w.C1_GOAL
+    else:
+        cfg, obs, init, goal = dict(w.C2, maxTreeSize=200000), w.c2_obstacles(1000), w.C2_INIT, w.C2_GOAL
+    ref = K.KGMT(**cfg, seed=11); ref.set_obstacles(obs); ref.begin(init, goal)
+    ranks = []
+    for g in range(world):
+        p = K.KGMT(**cfg, seed=11); p.set_obstacles(obs); p.begin(init, goal)
+        ranks.append(p)
+    deltas = [torch.zeros(ranks[0].shard_delta_ints(), dtype=torch.int32, device=dev) for _ in ranks]
+    for it in range(120):
+        want = ref.iterate()
+        got, infos, counts = _emulated_round(ranks, deltas, dev)
+        assert got == want, (it, got, want)
+        assert sum(counts) == want["accepted"]
+        # contiguous chunk ranges that tile the iteration
+        assert infos[0]["chunk_lo"] == 0 and all(a["chunk_hi"] == b["chunk_lo"] or b["chunk_hi"] == b["chunk_lo"]
+                                                  for a, b in zip(infos, infos[1:]))
+        if it < 6 or want["stop"] != 0:
+            for p in ranks:
+                _same_state(ref, p, want["tree_size"])
+        if want["stop"] != 0:
+            break
+    assert want["stop"] in (1, 2, 3, 4)
+    if want["stop"] == 1:
+        for p in ranks:
+            np.testing.assert_array_equal(ref.extract_path(), p.extract_path())
+
+
+def test_sharded_driver_single_process_and_mixed_with_cooperative_iterations():
+    """ShardedExpander (world 1, planner on torch's stream) == kgmt_plan; shard rounds and cooperative launches mix."""
+    cfg, obs = w.C1, w.C1_OBSTACLES
+    ref = K.KGMT(**cfg, seed=3); ref.set_obstacles(obs)
+    want = ref.plan(w.C1_INIT, w.C1_GOAL)
+    p = K.KGMT(**cfg, seed=3); p.set_obstacles(obs); p.begin(w.C1_INIT, w.C1_GOAL)
+    ex = ShardedExpander(p, timing=True)
+    st = ex.iterate(); st = ex.iterate()
+    assert "compute_ms" in st and st["comm_bytes"] == 0
+    st = p.iterate_many(2)                      # cooperative kernel continues from the sharded state
+    hist = ex.run()
+    r = p.result()
+    for k in ("stop", "iterations", "tree_size", "cost_to_goal", "goal_index", "expansions"):
+        assert r[k] == want[k], (k, r[k], want[k])
+    _same_state(ref, p, want["tree_size"])
+
+
+def test_forced_children_sweep_shape():
+    """config 5 shape: P parents seeded as the frontier, M = P * children candidates in one sharded iteration."""
+    obs = w.c2_obstacles(1000)
+    P, children = 4096, 64
+    M = P * children
+    cfg = dict(w.C1, maxTreeSize=M + P, numIterations=3)
+    parents = w.random_parents(P, obs, seed=7)
+    outs = []
+    for world in (1, 2):
+        ranks = []
+        for g in range(world):
+            p = K.KGMT(**cfg, seed=5, max_candidates=M); p.set_obstacles(obs)
+            p.seed_frontier(parents, w.C2_GOAL); p.set_children(children)
+            ranks.append(p)
+        deltas = [torch.zeros(ranks[0].shard_delta_ints(), dtype=torch.int32, device="cuda") for _ in ranks]
+        st, infos, counts = _emulated_round(ranks, deltas, torch.device("cuda", 0))
+        assert st["candidates"] == M and st["children"] == children
+        outs.append((st, ranks[0].export(K.ARR_SAMPLES)[:st["tree_size"]].copy(), ranks[0].export(K.ARR_PARENT)[:st["tree_size"]].copy()))
+    assert outs[0][0] == outs[1][0]
+    np.testing.assert_array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
+    np.testing.assert_array_equal(outs[0][2], outs[1][2])
