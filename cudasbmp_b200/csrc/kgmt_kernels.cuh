@@ -873,6 +873,9 @@ __global__ void shard_apply_kernel(const KArgs A, int* delta, size_t c2) {
     const unsigned stampNew = (unsigned)A.st->itr + 1u;
     const int nn = A.n * A.n;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    /* leave this iteration's scan block sums clean, as the cooperative kernel does (a later launch of it may follow) */
+    int* bs = A.blockSum + (size_t)(A.st->itr % 3) * A.blocksCap;
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < (size_t)A.blocksCap; b += stride) bs[b] = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < c2; i += stride) {
         int* d = delta + 4 * c1;
         const int a = d[i], v = d[c2 + i], iv = d[2 * c2 + i], sd = d[3 * c2 + i];

@@ -15,7 +15,7 @@ Q = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 inits, goals = w.random_queries(Q, w.C1_OBSTACLES)
 plan = K.KGMT(**w.C1, seed=1, device=local)
 plan.set_obstacles(w.C1_OBSTACLES)
-multi.plan_batch(plan, inits[:8 * world], goals[:8 * world], seeds=list(range(8 * world)))          # warm-up
+multi.plan_batch(plan, inits, goals, seeds=list(range(Q)))          # warm-up (allocates the per-query workspaces)
 torch.cuda.synchronize()
 if world > 1: dist.barrier()
 t0 = time.perf_counter()
