@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -114,6 +115,7 @@ static expand_fn expand_entry(int col, bool rec) {
         case COL_GRID_SMEM: return pick_expand<COL_GRID_SMEM>(rec);
         case COL_GRID_GLOBAL: return pick_expand<COL_GRID_GLOBAL>(rec);
         case COL_BRUTE_SMEM: return pick_expand<COL_BRUTE_SMEM>(rec);
+        case COL_BRUTE_STREAM: return pick_expand<COL_BRUTE_STREAM>(rec);
         default: return pick_expand<COL_BRUTE_GLOBAL>(rec);
     }
 }
@@ -153,7 +155,7 @@ static KArgs make_args(const kgmt_ctx* c) {
     A.obstacles = c->dObs; A.K = c->K;
     A.cellStart = c->dCellStart; A.cellItems = c->dCellItems; A.cullC = c->cullC;
     A.cullInvX = c->cullInvX; A.cullInvY = c->cullInvY; A.cellStartInts = c->cellStartInts; A.numItems = c->numItems;
-    A.obsTile = 0;
+    A.obsTile = (c->K + STREAM_TILE - 1) / STREAM_TILE;      /* tiles of the padded obstacle array */
     A.iterLog = c->iterLog;
     A.W = c->p.width; A.H = c->p.height; A.L = c->p.agent_length; A.R1Size = c->R1Size; A.R2Size = c->R2Size;
     A.goalX = c->goal[0]; A.goalY = c->goal[1]; A.goalR = c->p.goal_threshold;
@@ -170,8 +172,11 @@ static int configure(kgmt_ctx* ctx) {
     size_t colBytes = 0;
     int col;
     if (ctx->p.collision_mode == KGMT_COLLIDE_BRUTE) {
+        /* every obstacle, every step: one shared-memory piece while it fits the staging budget, else streamed through
+         * two 16 KB tiles by the TMA engine (occupancy stays at 4 CTAs per SM instead of 1) */
         colBytes = (size_t)ctx->K * 16;
-        col = (histBytes + colBytes <= MAX_DYN_SMEM) ? COL_BRUTE_SMEM : COL_BRUTE_GLOBAL;
+        if (colBytes <= limit) col = COL_BRUTE_SMEM;
+        else { col = COL_BRUTE_STREAM; colBytes = (size_t)2 * STREAM_TILE * 16; }
     } else {
         colBytes = (size_t)ctx->cellStartInts * 4 + (size_t)ctx->numItems * 16;
         col = (colBytes <= limit && histBytes + colBytes <= MAX_DYN_SMEM) ? COL_GRID_SMEM : COL_GRID_GLOBAL;
@@ -196,8 +201,12 @@ static int configure(kgmt_ctx* ctx) {
         ctx->shardGrid = std::max(o, 1) * ctx->numSMs;
     }
     if (occ < 1) return fail(ctx, KGMT_ERR_CUDA, "expand kernel does not fit on an SM (smem %zu B)", ctx->smemBytes);
-    ctx->gridLoop = occ * ctx->numSMs;
     ctx->gridMax = occ * ctx->numSMs;
+    /* persistent grid of the cooperative kernel: resident CTAs per SM (tuning knob: reserved[1], or the environment
+     * variable KGMT_CTAS_PER_SM for experiments; 0 = all that fit) */
+    int perSM = ctx->p.reserved[1];
+    if (perSM <= 0) { const char* e = getenv("KGMT_CTAS_PER_SM"); if (e) perSM = atoi(e); }
+    ctx->gridLoop = (perSM > 0 ? std::min(perSM, occ) : occ) * ctx->numSMs;
     ctx->configured = true;
     return KGMT_OK;
 }
@@ -258,12 +267,22 @@ static int build_cull_grid(kgmt_ctx* ctx) {
 
 static int install_obstacles(kgmt_ctx* ctx) {
     const int K = ctx->K;
-    if ((size_t)std::max(K, 1) > ctx->obsCap) {
+    /* the device copy is padded to whole stream tiles with boxes nothing can overlap (min = +inf, max = -inf) */
+    const size_t padded = (size_t)std::max((K + STREAM_TILE - 1) / STREAM_TILE, 1) * STREAM_TILE;
+    if (padded > ctx->obsCap) {
         if (ctx->dObs) cudaFree(ctx->dObs);
-        CU(cudaMalloc(&ctx->dObs, (size_t)std::max(K, 1) * 16));
-        ctx->obsCap = std::max(K, 1);
+        CU(cudaMalloc(&ctx->dObs, padded * 16));
+        ctx->obsCap = padded;
     }
-    if (K) CU(cudaMemcpyAsync(ctx->dObs, ctx->hObs.data(), (size_t)K * 16, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        std::vector<float> h(padded * 4);
+        if (K) memcpy(h.data(), ctx->hObs.data(), (size_t)K * 16);
+        for (size_t k = (size_t)K; k < padded; ++k) {
+            h[4 * k] = INFINITY; h[4 * k + 1] = INFINITY; h[4 * k + 2] = -INFINITY; h[4 * k + 3] = -INFINITY;
+        }
+        CU(cudaMemcpyAsync(ctx->dObs, h.data(), padded * 16, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     int rc = build_cull_grid(ctx);
     if (rc) return rc;
     return configure(ctx);

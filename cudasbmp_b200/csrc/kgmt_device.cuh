@@ -177,4 +177,42 @@ __device__ __forceinline__ bool propagate_edge(float4& s, const Controls& u, con
     return valid;
 }
 
+/* ---------------------------------------------------------- tile-streamed exhaustive test --
+ * The same edge (propagateAndCheck, statePropagator.cu:21-75) when the obstacle set does not fit shared memory in
+ * one piece: the obstacles stream through shared memory in tiles and the edge is re-integrated once per tile (the
+ * integration is a few dozen instructions per step against thousands of AABB tests per tile).  The reference exits at
+ * the FIRST step whose bbox overlaps ANY obstacle; the first such step is the minimum over the tiles of each tile's
+ * first overlapping step, so pass t only has to look at the steps before the best exit found so far. */
+struct EdgeExit { float4 s; int step; bool valid; };   /* state at exit, exit step (numDisc = ran to the end) */
+
+template <bool FIRST>
+__device__ __forceinline__ void edge_tile_pass(const float4 s0, const Controls& u, const DynParams& p, float dt, float tanS,
+                                               const float4* tile, int nObs, EdgeExit& e) {
+    const bool unitL = (p.L == 1.0f);
+    const CollideSmemAll col{tile, nObs};
+    CollideSmemAll::Cursor cur;
+    float x = s0.x, y = s0.y, th = s0.z, v = s0.w;
+    const int limit = FIRST ? p.numDisc : e.step;
+    for (int i = 0; i < limit; ++i) {
+        const float px = x, py = y;
+        const float sn = sinf(th), cs = cosf(th);
+        x = __fmaf_rn(dt, __fmul_rn(v, cs), x);
+        y = __fmaf_rn(dt, __fmul_rn(v, sn), y);
+        if (FIRST && (x <= 0.0f || x >= p.W || y <= 0.0f || y >= p.H)) {            /* :42-45 */
+            e.s = make_float4(x, y, th, v); e.step = i; e.valid = false;
+            return;
+        }
+        const float vl = unitL ? v : __fdiv_rn(v, p.L);
+        th = __fmaf_rn(dt, __fmul_rn(vl, tanS), th);
+        v = __fmaf_rn(u.a, dt, v);
+        const float bnx = (px > x) ? x : px, bxx = (px > x) ? px : x;
+        const float bny = (py > y) ? y : py, bxy = (py > y) ? py : y;
+        if (col.hit(cur, x, y, bnx, bny, bxx, bxy)) {                                 /* :61-64 */
+            e.s = make_float4(x, y, th, v); e.step = i; e.valid = false;
+            return;
+        }
+    }
+    if (FIRST) { e.s = make_float4(x, y, th, v); e.step = p.numDisc; e.valid = true; }
+}
+
 }  // namespace kgmt

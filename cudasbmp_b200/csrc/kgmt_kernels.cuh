@@ -45,7 +45,8 @@ constexpr int CHUNK = 32;                 /* candidates per chunk == one warp */
 constexpr int BLK_CHUNKS = 256;           /* chunks per scan block (one per thread of a CTA in phase B) */
 
 enum { STOP_RUNNING = 0, STOP_SOLVED = 1, STOP_TREE_FULL = 2, STOP_ITER_LIMIT = 3, STOP_FRONTIER_EMPTY = 4 };
-enum { COL_GRID_SMEM = 0, COL_GRID_GLOBAL = 1, COL_BRUTE_SMEM = 2, COL_BRUTE_GLOBAL = 3 };
+enum { COL_GRID_SMEM = 0, COL_GRID_GLOBAL = 1, COL_BRUTE_SMEM = 2, COL_BRUTE_GLOBAL = 3, COL_BRUTE_STREAM = 4 };
+constexpr int STREAM_TILE = 1024;         /* obstacles per streamed shared-memory tile (16 KB), double buffered */
 enum { FLAG_VALID = 1, FLAG_ACCEPT = 2 };
 
 /* planner scalars.  The first COPIED_WORDS ints are advanced identically by every CTA in shared memory and written
@@ -287,22 +288,39 @@ __device__ __forceinline__ IterView make_view(const KArgs& A, const DevState& S)
 /* ---------------------------------------------------------------- phase A: one chunk ---
  * 32 candidates, one per lane: stages 2-5a.  No communication outside the warp.
  * scoresOk (warp-uniform) remembers that this iteration's score buffer has been seen complete. */
-template <class Collide, bool RECORD, bool SHARD = false>
-__device__ __forceinline__ void expand_chunk(const KArgs& A, const IterView& it, const DynParams& dyn,
-                                             const Collide& col, int c, int lane, int* hV, int* hI, bool& scoresOk) {
+/* one candidate of a chunk between its stages */
+struct ChunkCand {
+    float4 x; Controls u; int parent; float parentCost; bool live, valid;
+};
+
+/* stage 2 + the parent read of stage 3 for lane `lane` of chunk c */
+__device__ __forceinline__ ChunkCand chunk_setup(const KArgs& A, const IterView& it, int c, int lane) {
+    ChunkCand cc;
     const int s = c * CHUNK + lane;
-    const bool live = s < it.M;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    Controls u{0.f, 0.f, 0.f, 0.f};
-    int parent = -1, r1 = -1, r2 = -1;
-    bool valid = false, accept = false;
-    float parentCost = 0.f;
+    cc.live = s < it.M;
+    cc.x = make_float4(0.f, 0.f, 0.f, 0.f);
+    cc.u = Controls{0.f, 0.f, 0.f, 0.f};
+    cc.parent = -1; cc.parentCost = 0.f; cc.valid = false;
+    if (cc.live) {
+        cc.parent = it.frontierStart + s / it.children;                    /* KGMT.cu:374-376 / :454 */
+        cc.x = __ldcg(&A.treeState[cc.parent]);                            /* L2-coherent: written by other SMs */
+        cc.parentCost = __ldcg(&A.treeCtrl[cc.parent]).w;
+        cc.u = sample_controls((uint32_t)s, it.key0);
+    }
+    return cc;
+}
+
+/* stage 5a for the chunk: region indices, counters, accept on the iteration-start snapshot, ballot compaction */
+template <bool RECORD, bool SHARD>
+__device__ __forceinline__ void chunk_finish(const KArgs& A, const IterView& it, const ChunkCand& cc, int c, int lane,
+                                             int* hV, int* hI, bool& scoresOk) {
+    const int s = c * CHUNK + lane;
+    const bool live = cc.live, valid = cc.valid;
+    const float4 x = cc.x;
+    const Controls u = cc.u;
+    int r1 = -1, r2 = -1;
+    bool accept = false;
     if (live) {
-        parent = it.frontierStart + s / it.children;                       /* KGMT.cu:374-376 / :454 */
-        x = __ldcg(&A.treeState[parent]);                                  /* L2-coherent: written by other SMs */
-        parentCost = __ldcg(&A.treeCtrl[parent]).w;
-        u = sample_controls((uint32_t)s, it.key0);
-        valid = propagate_edge(x, u, dyn, col);
         r1 = region_r1(x.x, x.y, A.R1Size, A.N);                           /* KGMT.cu:390 */
         r2 = region_r2(x.x, x.y, r1, A.R1Size, A.N, A.R2Size, A.n);        /* KGMT.cu:391 */
     }
@@ -338,7 +356,7 @@ __device__ __forceinline__ void expand_chunk(const KArgs& A, const IterView& it,
     const unsigned bal = __ballot_sync(0xffffffffu, accept);
     if (accept) {
         const int at = c * CHUNK + __popc(bal & ((1u << lane) - 1u));
-        const float cost = __fadd_rn(parentCost, u.duration);                      /* :585-586, :631-633 */
+        const float cost = __fadd_rn(cc.parentCost, u.duration);                   /* :585-586, :631-633 */
         __stcg(&it.stageState[at], x);
         __stcg(&it.stageCtrl[at], make_float4(u.a, u.steering, u.duration, cost));
         if (!SHARD && in_goal(x.x, x.y, A.goalX, A.goalY, A.goalR))               /* :589; min cost, then first in order */
@@ -351,9 +369,72 @@ __device__ __forceinline__ void expand_chunk(const KArgs& A, const IterView& it,
     if (RECORD && live) {
         A.candState[s] = x;
         A.candCtrl[s] = make_float4(u.a, u.steering, u.duration, u.u3);
-        A.candParent[s] = parent;
+        A.candParent[s] = cc.parent;
         A.candR1[s] = r1; A.candR2[s] = r2;
         A.candFlags[s] = (unsigned char)((valid ? FLAG_VALID : 0) | (accept ? FLAG_ACCEPT : 0));
+    }
+}
+
+/* ---------------------------------------------------------------- phase A: one chunk ---
+ * 32 candidates, one per lane: stages 2-5a.  No communication outside the warp.
+ * scoresOk (warp-uniform) remembers that this iteration's score buffer has been seen complete. */
+template <class Collide, bool RECORD, bool SHARD = false>
+__device__ __forceinline__ void expand_chunk(const KArgs& A, const IterView& it, const DynParams& dyn,
+                                             const Collide& col, int c, int lane, int* hV, int* hI, bool& scoresOk) {
+    ChunkCand cc = chunk_setup(A, it, c, lane);
+    if (cc.live) cc.valid = propagate_edge(cc.x, cc.u, dyn, col);
+    chunk_finish<RECORD, SHARD>(A, it, cc, c, lane, hV, hI, scoresOk);
+}
+
+/* ------------------------------------------- phase A with the obstacles STREAMED in tiles ----
+ * Exhaustive test when the obstacle set exceeds the shared-memory staging budget (BASELINE config 3).  The obstacle
+ * array cycles through two 16 KB shared-memory tiles filled by the TMA engine (cp.async.bulk + mbarrier); the CTA takes
+ * WARPS consecutive chunks at a time and all its warps walk the tile sequence together: wait(full) -> one pass of every
+ * edge over the tile (edge_tile_pass) -> the last warp to finish with a buffer re-arms it and issues the next load, so
+ * the copy of tile t+2 overlaps the tests against tile t+1. */
+struct TileStream {
+    float4* buf0; uint64_t* full; int* cnt;        /* two tiles back to back; full[2] mbarriers; cnt[2] warps done with a tile */
+    const float4* obstacles; int T;                /* global array padded to T * STREAM_TILE entries */
+    unsigned g;                                    /* tiles consumed so far by this CTA (uniform over its threads) */
+};
+
+__device__ __forceinline__ void tile_issue(const TileStream& ts, unsigned g) {
+    const int b = (int)(g & 1u);
+    mbar_expect_tx(&ts.full[b], STREAM_TILE * 16u);
+    bulk_g2s(ts.buf0 + b * STREAM_TILE, ts.obstacles + (size_t)(g % (unsigned)ts.T) * STREAM_TILE, STREAM_TILE * 16u, &ts.full[b]);
+}
+
+template <bool RECORD>
+__device__ __forceinline__ void stream_group(const KArgs& A, const IterView& it, const DynParams& dyn, TileStream& ts,
+                                             int base, int lane, int warp, int* hV, int* hI, bool& scoresOk) {
+    const int c = base + warp;
+    const bool chunkLive = c < it.numChunks;
+    ChunkCand cc = chunkLive ? chunk_setup(A, it, c, lane) : ChunkCand{};
+    const float dt = __fdiv_rn(cc.u.duration, (float)dyn.numDisc);
+    const float tanS = tanf(cc.u.steering);
+    const float4 s0 = cc.x;
+    EdgeExit e{s0, 0, false};
+    for (int t = 0; t < ts.T; ++t) {
+        const int b = (int)(ts.g & 1u);
+        mbar_wait(&ts.full[b], (ts.g >> 1) & 1u);
+        if (chunkLive && cc.live) {
+            if (t == 0) edge_tile_pass<true>(s0, cc.u, dyn, dt, tanS, ts.buf0 + b * STREAM_TILE, STREAM_TILE, e);
+            else if (e.step > 0) edge_tile_pass<false>(s0, cc.u, dyn, dt, tanS, ts.buf0 + b * STREAM_TILE, STREAM_TILE, e);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(&ts.cnt[b], 1) == WARPS - 1) {       /* every warp is done reading this buffer: refill it */
+                ts.cnt[b] = 0;
+                __threadfence_block();
+                tile_issue(ts, ts.g + 2u);
+            }
+        }
+        ts.g += 1u;
+    }
+    if (chunkLive) {
+        cc.x = e.s; cc.valid = e.valid;
+        chunk_finish<RECORD, false>(A, it, cc, c, lane, hV, hI, scoresOk);
     }
 }
 
@@ -426,6 +507,7 @@ struct ColSet {
     CollideGrid gridS, gridG;
     CollideSmemAll allS, allG;
     int* hV; int* hI;                       /* per-CTA R1 histograms (shared memory) */
+    TileStream stream;                      /* COL_BRUTE_STREAM only */
 };
 
 /* carve dynamic shared memory [R1 histograms][collision data] and stage the collision structure into it with
@@ -434,6 +516,7 @@ template <int COL>
 __device__ __forceinline__ ColSet stage_collision(const KArgs& A, unsigned char* smem_raw, uint64_t* sBar) {
     const int tid = threadIdx.x;
     ColSet cs;
+    cs.stream = TileStream{};
     cs.hV = reinterpret_cast<int*>(smem_raw);
     cs.hI = cs.hV + (A.useHist ? A.c1 : 0);
     unsigned char* colBase = smem_raw + (A.useHist ? ((2 * A.c1 * 4 + 15) & ~15) : 0);
@@ -461,6 +544,17 @@ __device__ __forceinline__ ColSet stage_collision(const KArgs& A, unsigned char*
             sObs = reinterpret_cast<const float4*>(colBase);
         }
     }
+    if (COL == COL_BRUTE_STREAM) {
+        /* two tiles + two 'full' mbarriers + two arrival counters; the first two loads go out at once */
+        __shared__ __align__(8) uint64_t sFull[2];
+        __shared__ int sCnt[2];
+        TileStream& ts = cs.stream;
+        ts.buf0 = reinterpret_cast<float4*>(colBase);
+        ts.full = sFull; ts.cnt = sCnt; ts.obstacles = A.obstacles; ts.T = A.obsTile; ts.g = 0u;
+        if (tid == 0) { mbar_init(&sFull[0], 1); mbar_init(&sFull[1], 1); sCnt[0] = 0; sCnt[1] = 0; mbar_fence_init(); }
+        __syncthreads();
+        if (tid == 0) { tile_issue(ts, 0u); tile_issue(ts, 1u); }
+    }
     cs.gridS = CollideGrid{sCellStart, sItems, A.cullC, A.cullInvX, A.cullInvY};
     cs.gridG = CollideGrid{A.cellStart, A.cellItems, A.cullC, A.cullInvX, A.cullInvY};
     cs.allS = CollideSmemAll{sObs, A.K};
@@ -468,8 +562,14 @@ __device__ __forceinline__ ColSet stage_collision(const KArgs& A, unsigned char*
     return cs;
 }
 
+/* a CTA must not exit with bulk copies still landing in its shared memory: wait for the two tiles in flight */
+__device__ __forceinline__ void stream_drain(const TileStream& ts) {
+    mbar_wait(&ts.full[ts.g & 1u], (ts.g >> 1) & 1u);
+    mbar_wait(&ts.full[(ts.g + 1u) & 1u], ((ts.g + 1u) >> 1) & 1u);
+}
+
 template <int COL, bool RECORD, class Group>
-__device__ void run_plan(const KArgs& A, int maxIters, Group& grp, const ColSet& cs) {
+__device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
     __shared__ int sRed[WARPS];
     __shared__ float sP[1024];
     __shared__ DevState S;
@@ -509,7 +609,21 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, const ColSet&
         /* ---- phase A: first chunk by position, further chunks by ticket (prefetched behind the current chunk) */
         if (A.useHist) for (int c = tid; c < 2 * A.c1; c += TILE) hV[c] = 0;
         __syncthreads();
-        {
+        if (COL == COL_BRUTE_STREAM) {
+            /* CTA-level tickets: WARPS consecutive chunks per fetch (the counter starts at totalWarps, as below) */
+            __shared__ int sBase;
+            bool scoresOk = false;
+            unsigned* ticket = A.ticket + (it.itr % 3);
+            int base = grp.rank * WARPS;
+            if (base < it.numChunks) wait_ge(&st->insertDone, S.blocksTotal);
+            while (base < it.numChunks) {
+                if (tid == 0) sBase = (int)atomicAdd(ticket, (unsigned)WARPS);
+                stream_group<RECORD>(A, it, dyn, cs.stream, base, lane, warp, hV, hI, scoresOk);
+                __syncthreads();
+                base = sBase;
+                __syncthreads();
+            }
+        } else {
             bool scoresOk = false;
             unsigned* ticket = A.ticket + (it.itr % 3);
             int c = gw;
@@ -521,7 +635,7 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, const ColSet&
                 if (COL == COL_GRID_SMEM)        expand_chunk<CollideGrid, RECORD>(A, it, dyn, colGridS, c, lane, hV, hI, scoresOk);
                 else if (COL == COL_GRID_GLOBAL) expand_chunk<CollideGrid, RECORD>(A, it, dyn, colGridG, c, lane, hV, hI, scoresOk);
                 else if (COL == COL_BRUTE_SMEM)  expand_chunk<CollideSmemAll, RECORD>(A, it, dyn, colAllS, c, lane, hV, hI, scoresOk);
-                else                             expand_chunk<CollideSmemAll, RECORD>(A, it, dyn, colAllG, c, lane, hV, hI, scoresOk);
+                else if (COL == COL_BRUTE_GLOBAL) expand_chunk<CollideSmemAll, RECORD>(A, it, dyn, colAllG, c, lane, hV, hI, scoresOk);
                 c = __shfl_sync(0xffffffffu, t, 0);
             }
         }
@@ -595,8 +709,9 @@ __global__ void __launch_bounds__(TILE) expand_kernel(const KArgs A, int maxIter
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t sBar;
     GridGroup grp;
-    const ColSet cs = stage_collision<COL>(A, smem_raw, &sBar);
+    ColSet cs = stage_collision<COL>(A, smem_raw, &sBar);
     run_plan<COL, RECORD, GridGroup>(A, maxIters, grp, cs);
+    if (COL == COL_BRUTE_STREAM) stream_drain(cs.stream);
 }
 
 /* ------------------------------------------------------- batched planning (config 4) ----
@@ -637,7 +752,7 @@ __global__ void __launch_bounds__(TILE) batch_kernel(const BatchArgs B) {
     ClusterGroup grp;
     const int tid = threadIdx.x;
     const int ws = (int)blockIdx.x / grp.size;
-    const ColSet cs = stage_collision<COL>(B.base, smem_raw, &sBar);
+    ColSet cs = stage_collision<COL>(B.base, smem_raw, &sBar);
 
     /* this workspace's arrays */
     KArgs A = B.base;

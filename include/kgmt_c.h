@@ -226,7 +226,7 @@ long long kgmt_launch_count(const kgmt_ctx* ctx);                /* kernels of t
  * iteration was finalized, candidates << 32 | accepted, then CTA 0's globaltimer at: iteration start, phase A done,
  * first grid barrier passed, phase B done, last grid barrier passed, 0} of the last plan; returns rows written */
 int  kgmt_iteration_log(kgmt_ctx* ctx, int enable, unsigned long long* out8, int max_rows);
-/* out8 = {collision back end (0 grid/smem, 1 grid/L1, 2 exhaustive/smem, 3 exhaustive/L1), cull cells per side,
+/* out8 = {collision back end (0 grid/smem, 1 grid/L1, 2 exhaustive/smem, 3 exhaustive/L1, 4 exhaustive/TMA-streamed tiles), cull cells per side,
  *         cull grid items, dynamic shared memory bytes, persistent grid size, SM count, R1 smem histograms, K} */
 int  kgmt_get_config(const kgmt_ctx* ctx, int* out8);
 
