@@ -242,6 +242,32 @@ def main():
     h2d = obs_host.nbytes + cfgd["cull_items"] * 16 + (cfgd["cull_cells"] ** 2 + 4) * 4 + 56 + 128
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- median time-to-first-solution, BASELINE config 1 (reference demo), 101 seeds: host wall clock from the
+    #      kgmt_plan call (state allocated, obstacles resident) to the host holding costToGoal != 0
+    ttfs = None
+    if rank == 0:
+        from cudasbmp_b200 import workloads as w
+        p1 = k.KGMT(**w.C1, seed=1, device=local)
+        p1.set_obstacles(w.C1_OBSTACLES)
+        for s in range(3):
+            p1.set_seed(1000 + s); p1.plan(w.C1_INIT, w.C1_GOAL)
+        walls, devs, unsolved = [], [], 0
+        for s in range(1, 102):
+            p1.set_seed(s)
+            tq = time.perf_counter()
+            r = p1.plan(w.C1_INIT, w.C1_GOAL)
+            dtq = time.perf_counter() - tq
+            if r["stop"] == 1:
+                walls.append(dtq * 1e3); devs.append(r["device_ms"])
+            else:
+                unsolved += 1
+        if walls:
+            ws = sorted(walls)
+            ttfs = {"config": "config1: reference demo map, init (5,5) goal (2,18), maxTree 30000", "seeds": 101,
+                    "solved": len(walls), "median_ms": statistics.median(walls), "p95_ms": ws[int(0.95 * (len(ws) - 1))],
+                    "device_median_ms": statistics.median(devs), "clock": "host wall around kgmt_plan"}
+        p1.close()
+
     # ---- max over ranks, sum of work
     t = torch.tensor([dev_ms, e2e_s, wall], dtype=torch.float64, device="cuda")
     c = torch.tensor([expansions, e2e_exp, accepted, launches], dtype=torch.float64, device="cuda")
@@ -269,6 +295,17 @@ def main():
     kern_ms = dev_ms / args.steps
     achieved = per_launch_exp * (B_EXP + B_INS * alpha) / (kern_ms * 1e-3) / 1e9
     solved = [r for r in results if r["stop"] == 1]
+    # ncu-derived per-launch figures of the dominant kernel (DRAM bytes, warp instructions per expansion)
+    prof = {}
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_inputs.json")))
+        if prof.get("workload") != args.workload or prof.get("collision") != args.collide:
+            prof = {}
+    except Exception:
+        prof = {}
+    sm_clock_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+    issue_peak = cfgd["sms"] * 4 * sm_clock_hz                 # one warp instruction per scheduler per clock
+    ipe = prof.get("warp_instructions_per_expansion")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -278,10 +315,18 @@ def main():
         "gpu_launches": int(launches_all),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                     "traffic": prof.get("dram_bytes_per_launch"), "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                      "kernel": "kgmt::expand_kernel<grid|brute, LOOP> (cooperative, one launch per plan)",
                      "algorithmic_bytes_per_expansion": B_EXP + B_INS * alpha, "accept_ratio": alpha,
-                     "note": "stages 2-4 are FP32-issue bound, not HBM bound (DESIGN.md); see profiles/"},
+                     "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, %s)" % prof.get("source"),
+                     "algorithmic_bytes_per_launch": per_launch_exp * (B_EXP + B_INS * alpha),
+                     "note": "stages 2-4 are FP32-issue bound, not HBM bound (DESIGN.md); see roofline_issue and profiles/"},
+        "roofline_issue": {"bound": "warp-instruction issue", "unit": "G warp-inst/s",
+                           "achieved": (per_launch_exp * ipe / (kern_ms * 1e-3) / 1e9) if ipe else None,
+                           "peak": issue_peak / 1e9, "frac": (per_launch_exp * ipe / (kern_ms * 1e-3) / issue_peak) if ipe else None,
+                           "warp_instructions_per_expansion": ipe, "avg_active_lanes": prof.get("avg_active_lanes"),
+                           "peak_source": "SMs x 4 schedulers x SM clock under load (nvidia-smi during the timed region)",
+                           "source": prof.get("source")},
         "plan": {"expansions_per_plan": exp_all / world / args.steps, "tree_size_mean": acc_all / world / args.steps + 1,
                  "iterations_mean": statistics.mean(r["iterations"] for r in results),
                  "solved": len(solved), "stops": sorted(set(r["stop"] for r in results)),
@@ -289,6 +334,7 @@ def main():
                  "host_wall_ms_per_plan": 1e3 * wall_max / args.steps},
         "collide_backend": cfgd,
     }
+    line["ttfs"] = ttfs
     if not args.no_cpu_baseline:
         try:
             base, _, _ = cpu_reference_rate(wl, seconds=12.0)
