@@ -44,6 +44,8 @@ struct kgmt_ctx {
     unsigned char* candFlags = nullptr;
     bool recordAllocated = false;
     unsigned* chunkMask = nullptr; int* blockSum = nullptr; unsigned* ticket = nullptr;
+    int* blockDone = nullptr; int* blockPrefix = nullptr; int* blockInserted = nullptr; PipeIter* pipeCtl = nullptr;   /* pipelined loop */
+    int pipe = 0;                      /* 1: kgmt_plan / kgmt_expand_iterations run the barrier-free loop (run_plan_pipe) */
     size_t chunksCap = 0, blocksCap = 0;
     float4 *stageState = nullptr, *stageCtrl = nullptr;
     unsigned long long* iterLog = nullptr;
@@ -103,6 +105,14 @@ static int fail(kgmt_ctx* c, int code, const char* fmt, ...) {
             return fail(ctx, KGMT_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
     } while (0)
 
+#ifdef KGMT_PIPE_PROF
+#define KGMT_ITERLOG_BYTES (256 * 64 + 8192 * 8 * 8)     /* + per-warp trace rows (debug build) */
+#else
+#define KGMT_ITERLOG_BYTES (256 * 64)
+#endif
+#ifndef KGMT_DEFAULT_LOOP
+#define KGMT_DEFAULT_LOOP 2          /* 1 = pipelined, 2 = grid barrier */
+#endif
 static const size_t MAX_DYN_SMEM = 227u * 1024u - 8u * 1024u;   /* leave room for static shared + reserve */
 
 /* -------------------------------------------------------------------------------- kernels table */
@@ -117,6 +127,17 @@ static expand_fn expand_entry(int col, bool rec) {
         case COL_BRUTE_SMEM: return pick_expand<COL_BRUTE_SMEM>(rec);
         case COL_BRUTE_STREAM: return pick_expand<COL_BRUTE_STREAM>(rec);
         default: return pick_expand<COL_BRUTE_GLOBAL>(rec);
+    }
+}
+template <int COL> static expand_fn pick_pipe(bool rec) {
+    return rec ? (expand_fn)expand_pipe_kernel<COL, true> : (expand_fn)expand_pipe_kernel<COL, false>;
+}
+static expand_fn pipe_entry(int col, bool rec) {
+    switch (col) {
+        case COL_GRID_SMEM: return pick_pipe<COL_GRID_SMEM>(rec);
+        case COL_GRID_GLOBAL: return pick_pipe<COL_GRID_GLOBAL>(rec);
+        case COL_BRUTE_SMEM: return pick_pipe<COL_BRUTE_SMEM>(rec);
+        default: return pick_pipe<COL_BRUTE_GLOBAL>(rec);
     }
 }
 typedef void (*prop_fn)(const KArgs, const float4*, long long, int, uint32_t, uint32_t);
@@ -151,6 +172,7 @@ static KArgs make_args(const kgmt_ctx* c) {
     A.chunkMask = c->chunkMask; A.blockSum = c->blockSum; A.ticket = c->ticket;
     A.stageState = c->stageState; A.stageCtrl = c->stageCtrl;
     A.chunksCap = (int)c->chunksCap; A.blocksCap = (int)c->blocksCap; A.maxCand = c->maxCand; A.totalWarps = c->gridLoop * WARPS;
+    A.blockDone = c->blockDone; A.blockPrefix = c->blockPrefix; A.blockInserted = c->blockInserted; A.pipe = c->pipeCtl; A.pipeMode = c->pipe;
     A.st = c->dState;
     A.obstacles = c->dObs; A.K = c->K;
     A.cellStart = c->dCellStart; A.cellItems = c->dCellItems; A.cullC = c->cullC;
@@ -184,9 +206,16 @@ static int configure(kgmt_ctx* ctx) {
     if (col == COL_GRID_GLOBAL || col == COL_BRUTE_GLOBAL) colBytes = 0;
     ctx->col = col;
     ctx->smemBytes = histBytes + colBytes;
+    /* loop flavour: reserved[2] = 1 barrier-free pipelined loop, 2 = grid-barrier loop, 0 = default (environment
+     * variable KGMT_PIPE, else pipelined); the tile-streamed back end only exists in the grid-barrier loop */
+    {
+        int want = ctx->p.reserved[2];
+        if (want == 0) { const char* e = getenv("KGMT_PIPE"); want = e ? (atoi(e) ? 1 : 2) : KGMT_DEFAULT_LOOP; }
+        ctx->pipe = (want == 1 && col != COL_BRUTE_STREAM) ? 1 : 0;
+    }
     int occ = 1 << 30;
     for (int rec = 0; rec < 2; ++rec) {
-        expand_fn f = expand_entry(col, rec != 0);
+        expand_fn f = ctx->pipe ? pipe_entry(col, rec != 0) : expand_entry(col, rec != 0);
         CU(cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemBytes));
         int o = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void*)f, TILE, ctx->smemBytes));
@@ -328,6 +357,9 @@ static int clear_state(kgmt_ctx* ctx, bool sync) {
     }
     CU(cudaMemsetAsync(ctx->mapSlab, 0, ctx->mapSlabInts * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->blockSum, 0, 3 * ctx->blocksCap * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->blockDone, 0, 3 * ctx->blocksCap * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->blockInserted, 0, 3 * ctx->blocksCap * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->pipeCtl, 0, 3 * sizeof(PipeIter), ctx->stream));
     fill_float_kernel<<<(2 * ctx->c1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->R1Score[0], 1.0f, (size_t)2 * ctx->c1);
     if (ctx->recordAllocated) {
         const size_t M = std::min((size_t)ctx->maxCand, ctx->dirtyCand);
@@ -353,6 +385,20 @@ static int clear_state(kgmt_ctx* ctx, bool sync) {
     }
     ctx->begun = false;
     ctx->haveCkpt = false;
+    return KGMT_OK;
+}
+
+/* scan/ticket/pipeline bookkeeping back to "between two iterations, nothing in flight" (after a restore or a sharded
+ * round, which do not run the planner loops' own recycling) */
+static int reset_loop_bookkeeping(kgmt_ctx* ctx) {
+    const unsigned t0 = ctx->pipe ? 0u : (unsigned)(ctx->gridLoop * WARPS);
+    const unsigned tk[4] = {t0, t0, t0, 0u};
+    CU(cudaMemcpyAsync(ctx->ticket, tk, 16, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->blockSum, 0, 3 * ctx->blocksCap * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->blockDone, 0, 3 * ctx->blocksCap * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->blockInserted, 0, 3 * ctx->blocksCap * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->pipeCtl, 0, 3 * sizeof(PipeIter), ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return KGMT_OK;
 }
 
@@ -415,6 +461,7 @@ void kgmt_destroy(kgmt_ctx* ctx) {
     cudaFree(ctx->candState); cudaFree(ctx->candCtrl); cudaFree(ctx->candParent);
     cudaFree(ctx->candR1); cudaFree(ctx->candR2); cudaFree(ctx->candFlags);
     cudaFree(ctx->chunkMask); cudaFree(ctx->blockSum); cudaFree(ctx->ticket);
+    cudaFree(ctx->blockDone); cudaFree(ctx->blockPrefix); cudaFree(ctx->blockInserted); cudaFree(ctx->pipeCtl);
     cudaFree(ctx->stageState); cudaFree(ctx->stageCtrl);
     cudaFree(ctx->dState); cudaFree(ctx->iterLog);
     if (ctx->hState) cudaFreeHost(ctx->hState);
@@ -483,6 +530,10 @@ int kgmt_create(const kgmt_params* p, kgmt_ctx** out) {
     CU(cudaMalloc(&ctx->chunkMask, 2 * ctx->chunksCap * 4));
     CU(cudaMalloc(&ctx->blockSum, 3 * ctx->blocksCap * 4));
     CU(cudaMalloc(&ctx->ticket, 4 * 4));
+    CU(cudaMalloc(&ctx->blockDone, 3 * ctx->blocksCap * 4));
+    CU(cudaMalloc(&ctx->blockPrefix, 3 * ctx->blocksCap * 4));
+    CU(cudaMalloc(&ctx->blockInserted, 3 * ctx->blocksCap * 4));
+    CU(cudaMalloc(&ctx->pipeCtl, 3 * sizeof(PipeIter)));
     CU(cudaMalloc(&ctx->stageState, 2 * (size_t)ctx->maxCand * 16));
     CU(cudaMalloc(&ctx->stageCtrl, 2 * (size_t)ctx->maxCand * 16));
     CU(cudaMemsetAsync(ctx->chunkMask, 0, 2 * ctx->chunksCap * 4, ctx->stream));
@@ -547,7 +598,8 @@ int kgmt_begin(kgmt_ctx* ctx, const float* initial7, const float* goal7) {
 
 static int launch_expand(kgmt_ctx* ctx, int maxIters) {
     KArgs A = make_args(ctx);
-    expand_fn f = expand_entry(ctx->col, ctx->p.record_candidates != 0);
+    expand_fn f = ctx->pipe ? pipe_entry(ctx->col, ctx->p.record_candidates != 0)
+                            : expand_entry(ctx->col, ctx->p.record_candidates != 0);
     void* args[] = {(void*)&A, (void*)&maxIters};
     CU(cudaLaunchCooperativeKernel((const void*)f, dim3(ctx->gridLoop), dim3(TILE), args, ctx->smemBytes, ctx->stream));
     ctx->launches += 1;
@@ -673,6 +725,7 @@ int kgmt_plan_batch(kgmt_ctx* ctx, const float* h_inits7, const float* h_goals7,
     B.base.stageState = b.stageState; B.base.stageCtrl = b.stageCtrl;
     B.base.candState = nullptr; B.base.candCtrl = nullptr; B.base.candParent = nullptr; B.base.candR1 = nullptr;
     B.base.candR2 = nullptr; B.base.candFlags = nullptr; B.base.iterLog = nullptr;
+    B.base.pipeMode = 0;                                   /* the cluster loop is the barrier loop: tickets start at totalWarps */
     B.Q = Q; B.numWorkspaces = numWs;
     B.initState = b.initState; B.initCtrl = b.initCtrl; B.goalXY = b.goalXY; B.seeds = b.seeds; B.states = b.states;
     B.paths = wantPath ? b.paths : nullptr; B.pathLen = b.pathLen; B.maxPath = wantPath;
@@ -804,6 +857,7 @@ int kgmt_shard_commit(kgmt_ctx* ctx, const void* d_recv, int cap_rows, const int
         ctx->launches += total > 0 ? 3 : 2;
     }
     ctx->shardAccepted = -1;
+    if (ctx->pipe) { int rc2 = reset_loop_bookkeeping(ctx); if (rc2) return rc2; }
     int rc = fetch_state(ctx);
     if (rc) return rc;
     if (out) {
@@ -927,10 +981,8 @@ int kgmt_restore(kgmt_ctx* ctx) {
     CU(cudaMemcpyAsync(ctx->mapSlab, ctx->mapSlabCkpt, ctx->mapSlabInts * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     *ctx->hState = ctx->ckptState;
     {   /* insertion bookkeeping back to "treeSize rows present, scan buffers clean" */
-        const unsigned tk[4] = {(unsigned)(ctx->gridLoop * WARPS), (unsigned)(ctx->gridLoop * WARPS), (unsigned)(ctx->gridLoop * WARPS), 0u};
-        CU(cudaMemcpyAsync(ctx->ticket, tk, 16, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemsetAsync(ctx->blockSum, 0, 3 * ctx->blocksCap * 4, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+        int rc2 = reset_loop_bookkeeping(ctx);
+        if (rc2) return rc2;
     }
     CU(cudaMemcpyAsync(ctx->dState, ctx->hState, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1144,13 +1196,17 @@ int kgmt_iteration_log(kgmt_ctx* ctx, int enable, unsigned long long* out8, int 
     if (!ctx) return KGMT_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
     if (enable && !ctx->iterLog) {
-        CU(cudaMalloc(&ctx->iterLog, 256 * 64));
-        CU(cudaMemset(ctx->iterLog, 0, 256 * 64));
+        CU(cudaMalloc(&ctx->iterLog, KGMT_ITERLOG_BYTES));
+        CU(cudaMemset(ctx->iterLog, 0, KGMT_ITERLOG_BYTES));
     }
     if (!out8 || max_rows <= 0 || !ctx->iterLog) return 0;
     int rc = fetch_state(ctx);
     if (rc) return rc;
+#ifdef KGMT_PIPE_PROF
+    const int n = std::min(256 + 8192, max_rows);   /* debug build: row 255 = per-phase warp-cycle totals, rows 256.. = warp traces */
+#else
     const int n = std::min(std::min(ctx->hState->iterationsDone, 255), max_rows);
+#endif
     CU(cudaMemcpy(out8, ctx->iterLog, (size_t)n * 64, cudaMemcpyDeviceToHost));
     return n;
 }

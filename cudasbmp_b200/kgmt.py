@@ -171,7 +171,8 @@ class KGMT:
 
     def __init__(self, width=20.0, height=20.0, N=16, n=8, numIterations=100, maxTreeSize=30000, numDisc=10,
                  agentLength=1.0, goalThreshold=0.5, *, seed=1, device=-1, max_candidates=0,
-                 collision_mode=COLLIDE_GRID, record_candidates=False, cull_cells=0, stage_limit_bytes=0):
+                 collision_mode=COLLIDE_GRID, record_candidates=False, cull_cells=0, stage_limit_bytes=0,
+                 ctas_per_sm=0, loop=0):
         L = load()
         p = default_params()
         p.width, p.height, p.N, p.n = width, height, N, n
@@ -180,6 +181,8 @@ class KGMT:
         p.seed, p.device, p.max_candidates = seed & 0xFFFFFFFF, device, max_candidates
         p.collision_mode, p.record_candidates, p.cull_cells = collision_mode, int(bool(record_candidates)), cull_cells
         p.reserved[0] = stage_limit_bytes
+        p.reserved[1] = ctas_per_sm          # 0 = as many as fit
+        p.reserved[2] = loop                 # planner loop: 0 default, 1 barrier-free pipelined, 2 grid barrier
         self.params = p
         self.N, self.n, self.max_tree = N, n, maxTreeSize
         self.max_cand = max_candidates if max_candidates > 0 else maxTreeSize
@@ -365,9 +368,10 @@ class KGMT:
 
     def iteration_log(self, enable=True):
         """Rows of 8 u64 (see kgmt_iteration_log) of the last plan; call once with enable to switch logging on."""
-        buf = (C.c_ulonglong * (8 * 256))()
-        n = self._ck(load().kgmt_iteration_log(self._h, int(enable), buf, 256))
-        return np.array(list(buf), dtype=np.uint64).reshape(-1, 8)[:n]
+        rows = int(os.environ.get("KGMT_ITERLOG_ROWS", "256"))
+        buf = (C.c_ulonglong * (8 * rows))()
+        n = self._ck(load().kgmt_iteration_log(self._h, int(enable), buf, rows))
+        return np.frombuffer(buf, dtype=np.uint64).reshape(-1, 8)[:n].copy()
 
     @property
     def launch_count(self):
