@@ -106,7 +106,7 @@ static int fail(kgmt_ctx* c, int code, const char* fmt, ...) {
     } while (0)
 
 #ifdef KGMT_PIPE_PROF
-#define KGMT_ITERLOG_BYTES (256 * 64 + 8192 * 8 * 8)     /* + per-warp trace rows (debug build) */
+#define KGMT_ITERLOG_BYTES (256 * 64 + 8192 * 32 * 8)    /* + per-warp trace rows of 32 words (debug build) */
 #else
 #define KGMT_ITERLOG_BYTES (256 * 64)
 #endif
@@ -235,7 +235,15 @@ static int configure(kgmt_ctx* ctx) {
      * variable KGMT_CTAS_PER_SM for experiments; 0 = all that fit) */
     int perSM = ctx->p.reserved[1];
     if (perSM <= 0) { const char* e = getenv("KGMT_CTAS_PER_SM"); if (e) perSM = atoi(e); }
-    ctx->gridLoop = (perSM > 0 ? std::min(perSM, occ) : occ) * ctx->numSMs;
+    if (perSM <= 0) {
+        /* no more CTAs than the largest iteration can feed with one chunk per warp: every resident CTA takes part in
+         * the grid barrier of every iteration, and small trees (config 1: 30 000 nodes) are barrier-latency bound
+         * (median time-to-first-solution 0.32 ms with 4 CTAs per SM, 0.27 ms with 1) */
+        const long long chunks = ((long long)ctx->maxCand + CHUNK - 1) / CHUNK;
+        const long long ctas = (chunks + WARPS - 1) / WARPS;
+        perSM = (int)std::max<long long>(1, std::min<long long>(occ, (ctas + ctx->numSMs - 1) / ctx->numSMs));
+    }
+    ctx->gridLoop = std::min(perSM, occ) * ctx->numSMs;
     ctx->configured = true;
     return KGMT_OK;
 }
@@ -1203,7 +1211,7 @@ int kgmt_iteration_log(kgmt_ctx* ctx, int enable, unsigned long long* out8, int 
     int rc = fetch_state(ctx);
     if (rc) return rc;
 #ifdef KGMT_PIPE_PROF
-    const int n = std::min(256 + 8192, max_rows);   /* debug build: row 255 = per-phase warp-cycle totals, rows 256.. = warp traces */
+    const int n = std::min(256 + 8192 * 4, max_rows);   /* debug build: row 255 = per-phase warp-cycle totals, rows 256.. = warp traces */
 #else
     const int n = std::min(std::min(ctx->hState->iterationsDone, 255), max_rows);
 #endif

@@ -757,6 +757,9 @@ __device__ __forceinline__ void st_relaxed_s32(int* p, int v) {
     asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+#ifndef KGMT_TRACE_ITR
+#define KGMT_TRACE_ITR 10
+#endif
 #ifndef PIPE_SLEEP_CAP
 #define PIPE_SLEEP_CAP 2048
 #endif
@@ -1138,8 +1141,14 @@ __device__ void run_plan_pipe(const KArgs& A, int maxIters, const ColSet& cs) {
 #ifdef KGMT_PIPE_PROF
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = clock64();
 #define PROF(k) { const long long now_ = clock64(); prof[k] += now_ - pt; pt = now_; }
+    unsigned long long* trow = A.iterLog ? A.iterLog + 8 * 256 + 32 * ((int)blockIdx.x * WARPS + (tid >> 5)) : nullptr;
+    int trk = 0;
+#define TR(slot) { if (trow && lane == 0 && V.itr == KGMT_TRACE_ITR) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); trow[slot] = t_; } }
+#define TRC(base) { if (trk < 8) TR((base) + 3 * trk) }
 #else
 #define PROF(k)
+#define TR(slot)
+#define TRC(base)
 #endif
     PipeView V = pipe_load_view(st, lane);
     int itersDone = 0;
@@ -1175,17 +1184,13 @@ __device__ void run_plan_pipe(const KArgs& A, int maxIters, const ColSet& cs) {
         if (t < 0 && lane == 0) { printf("bad first ticket: itr %d t %d heldT %d ticket now %u r %d\n", V.itr, t, heldT, *(volatile unsigned*)ticket, r); __trap(); }
 #endif
         PROF(7)
+        TR(0)
 #ifdef KGMT_PIPE_PROF
-        unsigned long long tr0 = 0, tr1 = 0, tr2 = 0; int trn = 0;
-        auto gt = [&]() { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); return t_; };
-        tr0 = gt();
+        trk = 0;
 #endif
         while (t < V.numChunks) {
             int tn = 0;
-#ifdef KGMT_PIPE_PROF
-            if (trn == 0) tr1 = gt();
-            ++trn;
-#endif
+            TRC(8)
             if (lane == 0) tn = (int)atomicAdd(ticket, 1u);
             ChunkCand cc;
             if (heldSpec && V.children == CHUNK && (V.mode == 1 || V.mode == 4)) {
@@ -1204,6 +1209,7 @@ __device__ void run_plan_pipe(const KArgs& A, int maxIters, const ColSet& cs) {
                 propagate(cc);
                 PROF(1)
             }
+            TRC(9)
             heldSpec = false;
             if (pendingDone >= 0) {
                 __syncwarp();
@@ -1215,6 +1221,10 @@ __device__ void run_plan_pipe(const KArgs& A, int maxIters, const ColSet& cs) {
 #endif
             chunk_finish<RECORD, false>(A, it, cc, t, lane, hV, hI, scoresOk);
             PROF(2)
+            TRC(10)
+#ifdef KGMT_PIPE_PROF
+            ++trk;
+#endif
             /* the chunk is signed off (blockDone) one chunk LATER, after the next chunk's stages 2-4: by then its
              * staging stores have long landed, so the release fence has nothing to wait for */
             pendingDone = t / BLK_CHUNKS;
@@ -1224,9 +1234,7 @@ __device__ void run_plan_pipe(const KArgs& A, int maxIters, const ColSet& cs) {
             if (t < 0 && lane == 0) { printf("bad next ticket: itr %d t %d ticket now %u r %d\n", V.itr, t, *(volatile unsigned*)ticket, r); __trap(); }
 #endif
         }
-#ifdef KGMT_PIPE_PROF
-        tr2 = gt();
-#endif
+        TR(1)
         heldT = -1; heldSpec = false;
         __syncwarp();
         if (pendingDone >= 0) {
@@ -1263,6 +1271,7 @@ __device__ void run_plan_pipe(const KArgs& A, int maxIters, const ColSet& cs) {
         }
 
         PROF(3)
+        TR(2)
         /* ---- ordered insertion (updateG) of this iteration's accepted rows, by the warps that ran out of chunks: units
          *      of 32 chunks by ticket; a unit waits until the rows before its block are known (prefix chain) */
         {
@@ -1287,12 +1296,7 @@ __device__ void run_plan_pipe(const KArgs& A, int maxIters, const ColSet& cs) {
             }
         }
         PROF(4)
-#ifdef KGMT_PIPE_PROF
-        if (V.itr == 10 && lane == 0 && A.iterLog) {
-            unsigned long long* row = A.iterLog + 8 * (256 + (int)blockIdx.x * WARPS + (tid >> 5));
-            row[0] = tr0; row[1] = tr1; row[2] = tr2; row[3] = gt(); row[4] = (unsigned long long)trn;
-        }
-#endif
+        TR(3)
         /* ---- one chunk of the NEXT iteration ahead of its publication */
         const int wantEpoch = V.iterationsDone + 1;
         rowsSeen = 0;
@@ -1315,6 +1319,7 @@ __device__ void run_plan_pipe(const KArgs& A, int maxIters, const ColSet& cs) {
             }
             spec = __shfl_sync(0xffffffffu, spec, 0);
             PROF(5)
+            TR(4)
             if (spec) {
                 fence_acq_rel();
                 IterView sv = it;           /* the next iteration if the 32-children policy holds (validated above) */
@@ -1324,6 +1329,7 @@ __device__ void run_plan_pipe(const KArgs& A, int maxIters, const ColSet& cs) {
                 propagate(held);
                 heldSpec = true;
                 PROF(1)
+                TR(5)
             }
         }
 
@@ -1332,14 +1338,9 @@ __device__ void run_plan_pipe(const KArgs& A, int maxIters, const ColSet& cs) {
             unsigned ns = 64;
             while (ld_relaxed_s32(&st->pipeEpoch) < wantEpoch) { __nanosleep(ns); if (ns < PIPE_SLEEP_CAP) ns <<= 1; }
         }
+        TR(6)
         __syncwarp();
         fence_acq_rel();
-#ifdef KGMT_PIPE_PROF
-        if (V.itr == 10 && lane == 0 && A.iterLog) {
-            unsigned long long* row = A.iterLog + 8 * (256 + (int)blockIdx.x * WARPS + (tid >> 5));
-            row[5] = gt();
-        }
-#endif
         V = pipe_load_view(st, lane);
         itersDone += 1;
         if (V.stop == STOP_RUNNING) pipe_scores_help(A, V.itr, A.pipe + V.itr % 3, sP, lane);
