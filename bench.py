@@ -128,6 +128,31 @@ def cpu_reference_rate(wl, seconds=12.0, threads=None):
                        % (M2, wl["label"].split(":")[0], sec2)), M2, sec2
 
 
+def ref_cuda_rate(wl):
+    """Baseline A of BASELINE.json: the reference's OWN propagateG kernel (unmodified sources recompiled for sm_100a,
+    oracle/_ref/libref_gpu.so, cuRAND Philox states) on the same obstacle map, CUDA-event time of stages 2-5a for
+    30 000 parents x 32 children (its largest launch, KGMT.cu:160-173)."""
+    try:
+        from oracle import pyoracle as po
+        from cudasbmp_b200 import workloads as w
+        if po.ref_gpu() is None:
+            return {"value": None, "unit": UNIT, "kind": "unavailable", "sample": "oracle/_ref/libref_gpu.so missing"}
+        cfg, obs = wl["cfg"], wl["obstacles"]
+        P = 30000
+        parents = w.random_parents(P, obs, seed=7)
+        N, n = 16, 8
+        c1, c2 = N * N, N * N * n * n
+        maps = {k: np.zeros(c1 if k.startswith("R1") else c2, dtype=np.int32)
+                for k in ("R1", "R2", "R1Valid", "R2Valid", "R1Invalid", "R2Invalid", "R1Avail", "R2Avail")}
+        _, _, _, ms = po.ref_gpu_expand(1, 32, parents, np.arange(P, dtype=np.int32), maps, np.ones(c1, np.float32), N, n,
+                                        cfg["width"] / N, cfg["width"] / (N * n), cfg["numDisc"], cfg["agentLength"], obs,
+                                        cfg["width"], cfg["height"], 99, reps=5)
+        return {"value": P * 32 / ms * 1e3, "unit": UNIT, "kind": "reference CUDA kernel propagateG recompiled for sm_100a",
+                "sample": "%d parents x 32 children on the %s map, %.3f ms per launch (best of 5)" % (P, wl["label"].split(":")[0], ms)}
+    except Exception as e:
+        return {"value": None, "unit": UNIT, "kind": "unavailable", "sample": repr(e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -335,6 +360,8 @@ def main():
         "collide_backend": cfgd,
     }
     line["ttfs"] = ttfs
+    if not args.no_cpu_baseline:
+        line["ref_cuda_baseline"] = ref_cuda_rate(wl)
     if not args.no_cpu_baseline:
         try:
             base, _, _ = cpu_reference_rate(wl, seconds=12.0)

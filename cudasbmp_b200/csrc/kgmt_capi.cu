@@ -270,8 +270,11 @@ static int build_cull_grid(kgmt_ctx* ctx) {
             for (int x = x0; x <= x1; ++x) start[(size_t)y * C + x + 1] += 1;
     }
     for (size_t i = 0; i < (size_t)C * C; ++i) start[i + 1] += start[i];
-    const int numItems = start[(size_t)C * C];
-    std::vector<float> items((size_t)std::max(numItems, 1) * 4, 0.0f);
+    const int realItems = start[(size_t)C * C];
+    const int numItems = realItems + 1;          /* + one box nothing overlaps: the cell walk may read one entry past a list */
+    std::vector<float> items((size_t)numItems * 4, 0.0f);
+    items[(size_t)realItems * 4] = INFINITY; items[(size_t)realItems * 4 + 1] = INFINITY;
+    items[(size_t)realItems * 4 + 2] = -INFINITY; items[(size_t)realItems * 4 + 3] = -INFINITY;
     std::vector<int> fill(start.begin(), start.end() - 1);
     for (int k = 0; k < K; ++k) {
         const int x0 = cull_cell(o[4 * k], invX, C), x1 = cull_cell(o[4 * k + 2], invX, C);
@@ -283,7 +286,7 @@ static int build_cull_grid(kgmt_ctx* ctx) {
             }
     }
     const int startInts = (int)((start.size() + 3) & ~(size_t)3);
-    start.resize(startInts, numItems);
+    start.resize(startInts, realItems);
     if ((size_t)startInts > ctx->cellStartCap) {
         if (ctx->dCellStart) cudaFree(ctx->dCellStart);
         CU(cudaMalloc(&ctx->dCellStart, (size_t)startInts * 4));

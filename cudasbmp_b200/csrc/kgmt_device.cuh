@@ -137,7 +137,12 @@ struct CollideGrid {
         for (int cy = cy0; cy <= cy1 && !h; ++cy) {
             const int row = cy * C;
             const int e = cellStart[row + cx1 + 1];
-            for (int k = cellStart[row + cx0]; k < e && !h; ++k) h = aabb_overlap(bnx, bny, bxx, bxy, items[k]);
+            int k = cellStart[row + cx0];
+            /* two items per trip: the list ends with one never-overlapping entry, so items[k + 1] is always readable */
+            for (; k < e && !h; k += 2) {
+                const float4 o0 = items[k], o1 = items[k + 1];
+                h = aabb_overlap(bnx, bny, bxx, bxy, o0) | ((k + 1 < e) & aabb_overlap(bnx, bny, bxx, bxy, o1));
+            }
         }
         return h;
     }

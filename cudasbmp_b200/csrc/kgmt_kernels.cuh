@@ -470,6 +470,18 @@ __device__ __forceinline__ void stream_group(const KArgs& A, const IterView& it,
     }
 }
 
+/* position of the r-th (0-based) set bit of m: five popcount halvings */
+__device__ __forceinline__ int nth_set_bit(unsigned m, int r) {
+    int pos = 0;
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) {
+        const unsigned lo = m & ((1u << w) - 1u);
+        const int c = __popc(lo);
+        if (r >= c) { r -= c; m >>= w; pos += w; } else { m = lo; }
+    }
+    return pos;
+}
+
 /* -------------------------------------------------------- phase B: one scan block ------
  * updateG (KGMT.cu:555-591) for the accepted candidates of 256 consecutive chunks.  Thread t
  * loads the ballot of chunk blk*256+t; a CTA-wide scan of the popcounts orders the rows; each
@@ -506,7 +518,7 @@ __device__ __forceinline__ void insert_block(const KArgs& A, const IterView& it,
         const int excl = __shfl_sync(0xffffffffu, incl - cnt, i);
         if (q < W) {
             const int r = q - excl;
-            const int bit = (int)__fns(m, 0, r + 1);
+            const int bit = nth_set_bit(m, r);
             const int ci = c0 + i;
             const int slot = ci * CHUNK + bit;
             const float4 x = __ldcg(&it.stageState[ci * CHUNK + r]);
@@ -892,18 +904,6 @@ __device__ __forceinline__ void pipe_rows(const KArgs& A, const IterView& it, Pi
         }
         if (!__shfl_sync(0xffffffffu, again, 0)) return;
     }
-}
-
-/* position of the r-th (0-based) set bit of m: five popcount halvings */
-__device__ __forceinline__ int nth_set_bit(unsigned m, int r) {
-    int pos = 0;
-#pragma unroll
-    for (int w = 16; w > 0; w >>= 1) {
-        const unsigned lo = m & ((1u << w) - 1u);
-        const int c = __popc(lo);
-        if (r >= c) { r -= c; m >>= w; pos += w; } else { m = lo; }
-    }
-    return pos;
 }
 
 constexpr int SUBS = BLK_CHUNKS / 32;     /* insertion units per scan block */
@@ -1599,7 +1599,7 @@ __global__ void __launch_bounds__(TILE) shard_pack_kernel(const KArgs A, int blk
             const int excl = __shfl_sync(0xffffffffu, incl - cnt, i);
             if (q < W) {
                 const int r = q - excl;
-                const int bit = (int)__fns(m, 0, r + 1);
+                const int bit = nth_set_bit(m, r);
                 const int ci = c0 + i;
                 sendState[dst0 + q] = __ldcg(&stageState[ci * CHUNK + r]);
                 sendCtrl[dst0 + q] = __ldcg(&stageCtrl[ci * CHUNK + r]);
