@@ -85,6 +85,14 @@ struct kgmt_ctx {
     /* sharded expansion (kgmt_shard_*) */
     int* shardPrefix = nullptr; int* shardTotal = nullptr; int* hShardTotal = nullptr;   /* [blocksCap], [1], pinned [1] */
     int shardBlkLo = 0, shardBlkHi = 0, shardAccepted = -1, shardGrid = 0;
+    /* sharded expansion over peer memory (kgmt_peer_*) */
+    struct Peer {
+        int rank = -1, world = 0, seq = 0; bool ipc = false, inFlight = false;
+        unsigned char* block = nullptr; size_t blockBytes = 0, mailOff = 0;     /* [delta slab | mailbox[PEER_MAX]] */
+        PeerPlan* plan = nullptr; PeerPlan* hPlan = nullptr;                    /* device, pinned host */
+        void* opened[PEER_MAX][5] = {};                                          /* cudaIpcOpenMemHandle results to close */
+        PeerArgs args{};
+    } peer;
     DevState resetState{};
     char err[512] = {0};
 };
@@ -467,6 +475,7 @@ void kgmt_destroy(kgmt_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    kgmt_peer_detach(ctx);
     cudaFree(ctx->treeState); cudaFree(ctx->treeCtrl); cudaFree(ctx->treeParent);
     cudaFree(ctx->mapSlab); cudaFree(ctx->mapSlabCkpt);
     cudaFree(ctx->candState); cudaFree(ctx->candCtrl); cudaFree(ctx->candParent);
@@ -482,6 +491,8 @@ void kgmt_destroy(kgmt_ctx* ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+    cudaFree(ctx->peer.block); cudaFree(ctx->peer.plan);
+    if (ctx->peer.hPlan) cudaFreeHost(ctx->peer.hPlan);
     cudaFree(ctx->shardPrefix); cudaFree(ctx->shardTotal);
     if (ctx->hShardTotal) cudaFreeHost(ctx->hShardTotal);
     delete ctx;
@@ -871,6 +882,183 @@ int kgmt_shard_commit(kgmt_ctx* ctx, const void* d_recv, int cap_rows, const int
     if (ctx->pipe) { int rc2 = reset_loop_bookkeeping(ctx); if (rc2) return rc2; }
     int rc = fetch_state(ctx);
     if (rc) return rc;
+    if (out) {
+        const DevState& s = *ctx->hState;
+        out->iteration = s.lastItr; out->mode = s.lastMode; out->children = s.lastChildren; out->frontier = s.lastFrontier;
+        out->candidates = s.lastM; out->accepted = s.lastAccepted; out->tree_size = s.treeSize; out->stop = s.stop;
+        out->cost_to_goal = s.costToGoal; out->goal_index = s.goalIdx;
+    }
+    return KGMT_OK;
+}
+
+/* ---- sharded expansion over peer memory (NVLink / NVSwitch; SURVEY.md §8e, second mode, without NCCL) ------------ */
+static int peer_alloc(kgmt_ctx* ctx) {
+    kgmt_ctx::Peer& pr = ctx->peer;
+    if (pr.block) return KGMT_OK;
+    const size_t deltaBytes = kgmt_shard_delta_ints(ctx) * 4;
+    pr.mailOff = (deltaBytes + 255) & ~(size_t)255;
+    pr.blockBytes = std::max<size_t>(pr.mailOff + PEER_MAX * sizeof(PeerMail), (size_t)2 << 20);   /* its own allocation granule */
+    CU(cudaMalloc(&pr.block, pr.blockBytes));
+    CU(cudaMemset(pr.block, 0, pr.blockBytes));
+    CU(cudaMalloc(&pr.plan, sizeof(PeerPlan)));
+    CU(cudaMemset(pr.plan, 0, sizeof(PeerPlan)));
+    CU(cudaHostAlloc(&pr.hPlan, sizeof(PeerPlan), cudaHostAllocDefault));
+    if (!ctx->shardPrefix) {
+        CU(cudaMalloc(&ctx->shardPrefix, ctx->blocksCap * 4));
+        CU(cudaMalloc(&ctx->shardTotal, 4));
+        CU(cudaHostAlloc(&ctx->hShardTotal, 4, cudaHostAllocDefault));
+    }
+    return KGMT_OK;
+}
+
+size_t kgmt_peer_handle_bytes(void) { return 5 * sizeof(cudaIpcMemHandle_t); }
+
+/* handles of the five allocations a peer maps: tree state, tree ctrl, tree parent, map slab, exchange block */
+int kgmt_peer_export(kgmt_ctx* ctx, void* out_handles, size_t bytes) {
+    if (!ctx || !out_handles || bytes < kgmt_peer_handle_bytes()) return fail(ctx, KGMT_ERR_INVALID, "handle buffer too small");
+    CU(cudaSetDevice(ctx->device));
+    int rc = peer_alloc(ctx);
+    if (rc) return rc;
+    cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)out_handles;
+    CU(cudaIpcGetMemHandle(&h[0], ctx->treeState));
+    CU(cudaIpcGetMemHandle(&h[1], ctx->treeCtrl));
+    CU(cudaIpcGetMemHandle(&h[2], ctx->treeParent));
+    CU(cudaIpcGetMemHandle(&h[3], ctx->mapSlab));
+    CU(cudaIpcGetMemHandle(&h[4], ctx->peer.block));
+    return KGMT_OK;
+}
+
+static void peer_set(kgmt_ctx* ctx, int p, void* ts, void* tc, void* tp, void* ms, void* blk) {
+    PeerArgs& a = ctx->peer.args;
+    a.treeState[p] = (float4*)ts; a.treeCtrl[p] = (float4*)tc; a.treeParent[p] = (int*)tp; a.mapSlab[p] = (int*)ms;
+    a.delta[p] = (int*)blk; a.mail[p] = (PeerMail*)((unsigned char*)blk + ctx->peer.mailOff);
+}
+
+int kgmt_peer_detach(kgmt_ctx* ctx) {
+    if (!ctx) return KGMT_ERR_INVALID;
+    kgmt_ctx::Peer& pr = ctx->peer;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (pr.ipc)
+        for (int p = 0; p < PEER_MAX; ++p)
+            for (int k = 0; k < 5; ++k)
+                if (pr.opened[p][k]) { cudaIpcCloseMemHandle(pr.opened[p][k]); pr.opened[p][k] = nullptr; }
+    pr.rank = -1; pr.world = 0; pr.ipc = false; pr.inFlight = false;
+    return KGMT_OK;
+}
+
+/* all_handles: world x kgmt_peer_handle_bytes(), rank-major, as gathered from every rank's kgmt_peer_export */
+int kgmt_peer_attach(kgmt_ctx* ctx, int rank, int world, const void* all_handles) {
+    if (!ctx || !all_handles || world < 1 || world > PEER_MAX || rank < 0 || rank >= world) return fail(ctx, KGMT_ERR_INVALID, "bad peer arguments");
+    CU(cudaSetDevice(ctx->device));
+    int rc = peer_alloc(ctx);
+    if (rc) return rc;
+    kgmt_peer_detach(ctx);
+    kgmt_ctx::Peer& pr = ctx->peer;
+    pr.args = PeerArgs{};
+    const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)all_handles;
+    for (int p = 0; p < world; ++p) {
+        if (p == rank) { peer_set(ctx, p, ctx->treeState, ctx->treeCtrl, ctx->treeParent, ctx->mapSlab, pr.block); continue; }
+        void* ptr[5] = {};
+        for (int k = 0; k < 5; ++k) {
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr[k], h[p * 5 + k], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return fail(ctx, KGMT_ERR_COMM, "cudaIpcOpenMemHandle(rank %d, array %d): %s", p, k, cudaGetErrorString(e));
+            pr.opened[p][k] = ptr[k];
+        }
+        peer_set(ctx, p, ptr[0], ptr[1], ptr[2], ptr[3], ptr[4]);
+    }
+    pr.rank = rank; pr.world = world; pr.seq = 0; pr.ipc = true;
+    pr.args.rank = rank; pr.args.world = world; pr.args.plan = pr.plan;
+    return KGMT_OK;
+}
+
+/* the same wiring between contexts of ONE process (tests; several contexts may share a device) */
+int kgmt_peer_attach_local(kgmt_ctx* ctx, int rank, int world, kgmt_ctx* const* peers) {
+    if (!ctx || !peers || world < 1 || world > PEER_MAX || rank < 0 || rank >= world || peers[rank] != ctx)
+        return fail(ctx, KGMT_ERR_INVALID, "bad peer arguments");
+    CU(cudaSetDevice(ctx->device));
+    kgmt_peer_detach(ctx);
+    kgmt_ctx::Peer& pr = ctx->peer;
+    pr.args = PeerArgs{};
+    for (int p = 0; p < world; ++p) {
+        kgmt_ctx* o = peers[p];
+        if (!o || o->c1 != ctx->c1 || o->c2 != ctx->c2 || o->p.max_tree_size != ctx->p.max_tree_size)
+            return fail(ctx, KGMT_ERR_INVALID, "peer %d has a different configuration", p);
+        cudaSetDevice(o->device);
+        int rc = peer_alloc(o);
+        cudaSetDevice(ctx->device);
+        if (rc) return fail(ctx, rc, "peer %d: %s", p, o->err);
+        if (o->device != ctx->device) {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, ctx->device, o->device);
+            if (!can) return fail(ctx, KGMT_ERR_COMM, "device %d cannot map device %d", ctx->device, o->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, KGMT_ERR_COMM, "peer access: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        peer_set(ctx, p, o->treeState, o->treeCtrl, o->treeParent, o->mapSlab, o->peer.block);
+    }
+    pr.rank = rank; pr.world = world; pr.seq = 0; pr.ipc = false;
+    pr.args.rank = rank; pr.args.world = world; pr.args.plan = pr.plan;
+    return KGMT_OK;
+}
+
+/* enqueue ONE expansion iteration across the attached ranks (every rank must call it for the same iteration) */
+int kgmt_peer_expand_begin(kgmt_ctx* ctx) {
+    if (!ctx) return KGMT_ERR_INVALID;
+    kgmt_ctx::Peer& pr = ctx->peer;
+    if (pr.rank < 0) return fail(ctx, KGMT_ERR_STATE, "kgmt_peer_expand_begin before kgmt_peer_attach");
+    if (!ctx->begun) return fail(ctx, KGMT_ERR_STATE, "kgmt_peer_expand_begin before kgmt_begin / kgmt_seed_frontier");
+    if (pr.inFlight) return fail(ctx, KGMT_ERR_STATE, "kgmt_peer_expand_begin twice without kgmt_peer_expand_end");
+    CU(cudaSetDevice(ctx->device));
+    const DevState& s = *ctx->hState;
+    if (s.stop != STOP_RUNNING) { pr.inFlight = true; return KGMT_OK; }      /* nothing to run; _end reports the stop */
+    const int rank = pr.rank, world = pr.world;
+    const int numBlocks = (s.numChunks + BLK_CHUNKS - 1) / BLK_CHUNKS;
+    const int base = numBlocks / world, rem = numBlocks % world;
+    const int bLo = rank * base + std::min(rank, rem), bHi = bLo + base + (rank < rem ? 1 : 0);
+    const int cLo = bLo * BLK_CHUNKS, cHi = std::min(bHi * BLK_CHUNKS, s.numChunks);
+    const int chunks = std::max(cHi - cLo, 0);
+    cudaStream_t st = ctx->stream;
+    pr.seq += 1;
+    pr.args.seq = pr.seq;
+    const KArgs As = make_shard_args(ctx, (int*)pr.block);
+    const KArgs A = make_args(ctx);
+    const int grid = std::max(1, std::min(ctx->shardGrid, (chunks + WARPS - 1) / WARPS));
+    shard_reset_kernel<<<32, 256, 0, st>>>(As, grid * WARPS);
+    if (chunks > 0) shard_entry(ctx->col)<<<grid, TILE, ctx->smemBytes, st>>>(As, cLo, cHi);
+    shard_prefix_kernel<<<1, TILE, 0, st>>>(As, bLo, bHi, ctx->shardPrefix, ctx->shardTotal);
+    peer_counts_kernel<<<1, 32, 0, st>>>(pr.args, ctx->shardTotal);
+    if (bHi > bLo) peer_pack_kernel<<<std::min(bHi - bLo, ctx->numSMs * 8), TILE, 0, st>>>(A, pr.args, bLo, bHi, ctx->shardPrefix);
+    {
+        const size_t total = kgmt_shard_delta_ints(ctx);
+        const size_t per = total / world, extra = total % world;
+        const size_t lo = rank * per + std::min<size_t>(rank, extra), hi = lo + per + ((size_t)rank < extra ? 1 : 0);
+        if (hi > lo)
+            peer_reduce_kernel<<<(unsigned)std::min<size_t>((hi - lo + 255) / 256, (size_t)ctx->numSMs * 8), 256, 0, st>>>(A, pr.args, ctx->c2, lo, hi);
+    }
+    peer_barrier_kernel<<<1, 32, 0, st>>>(pr.args);
+    recount_cov_kernel<<<ctx->c1, 128, 0, st>>>(A);
+    CU(cudaMemsetAsync(pr.block, 0, kgmt_shard_delta_ints(ctx) * 4, st));
+    peer_finalize_kernel<<<1, TILE, 0, st>>>(A, pr.args);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(pr.hPlan, pr.plan, sizeof(PeerPlan), cudaMemcpyDeviceToHost, st));
+    ctx->launches += 9;
+    pr.inFlight = true;
+    return KGMT_OK;
+}
+
+int kgmt_peer_expand_end(kgmt_ctx* ctx, kgmt_iter_stats* out) {
+    if (!ctx) return KGMT_ERR_INVALID;
+    kgmt_ctx::Peer& pr = ctx->peer;
+    if (!pr.inFlight) return fail(ctx, KGMT_ERR_STATE, "kgmt_peer_expand_end without kgmt_peer_expand_begin");
+    CU(cudaSetDevice(ctx->device));
+    pr.inFlight = false;
+    const bool ran = ctx->hState->stop == STOP_RUNNING;
+    int rc = fetch_state(ctx);
+    if (rc) return rc;
+    if (ran && pr.hPlan->err) return fail(ctx, KGMT_ERR_COMM, "a peer did not arrive within 5 s (rank %d of %d, exchange %d)", pr.rank, pr.world, pr.seq);
+    if (ran && ctx->pipe) { rc = reset_loop_bookkeeping(ctx); if (rc) return rc; }
     if (out) {
         const DevState& s = *ctx->hState;
         out->iteration = s.lastItr; out->mode = s.lastMode; out->children = s.lastChildren; out->frontier = s.lastFrontier;

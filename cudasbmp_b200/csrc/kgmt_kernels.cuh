@@ -1696,6 +1696,219 @@ __global__ void __launch_bounds__(TILE) shard_finalize_kernel(const KArgs A, con
     if (tid == 0) { st->scoreReady = S.itr; st->insertDone = S.blocksTotal; }
 }
 
+/* ------------------------- sharded expansion over PEER MEMORY (NVLink / NVSwitch, no NCCL) ----
+ * The same split as above, but the exchange is done by the kernels themselves through pointers into the other GPUs'
+ * memory (cudaIpc handles, or the same process in the tests): per iteration
+ *   shard_expand + shard_prefix            local, as above (deltas into this rank's slab)
+ *   peer_counts      one warp: writes this rank's accepted count into every peer's mailbox (system-scope release),
+ *                    waits for every peer's count -> base = rows of lower ranks, total = rows of all ranks
+ *   peer_pack        accepted rows of this rank, candidate order, written STRAIGHT INTO EVERY RANK'S TREE at
+ *                    treeSize + base + local position (float4 state, float4 ctrl+cost, parent link): the all-gather and
+ *                    the insertion are one pass of stores over NVLink
+ *   peer_reduce      all-reduce of the counter deltas as reduce-scatter + all-gather over peer loads/stores: this rank
+ *                    owns a contiguous 1/world of the cells, sums every rank's delta for them and writes the new counter
+ *                    values (and first-reached stamps) into every rank's maps
+ *   peer_barrier     one warp: system fence, posts this rank's goal candidate, waits for every peer -> global goal
+ *   recount_cov, peer_finalize             local: R1Cov from the stamps, planner scalars, next scores
+ * Replicas stay bit-identical to the single-GPU run for the same reason as with NCCL: rank-major = candidate order. */
+constexpr int PEER_MAX = 16;
+struct PeerMail { unsigned long long goal; int count; int seq1; int seq2; int pad; };      /* 24 B -> padded to 32 */
+struct PeerPlan { unsigned long long goalLocal, goalGlobal; int base, total, err, pad; int counts[PEER_MAX]; };
+struct PeerArgs {
+    int rank, world, seq;
+    float4* treeState[PEER_MAX]; float4* treeCtrl[PEER_MAX]; int* treeParent[PEER_MAX];
+    int* mapSlab[PEER_MAX]; int* delta[PEER_MAX]; PeerMail* mail[PEER_MAX];     /* [p] = rank p's arrays as mapped on this device */
+    PeerPlan* plan;                                                             /* local */
+};
+
+__device__ __forceinline__ void st_release_sys_s32(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+/* wait until *p == want, at most ~5 s (a peer that never arrives must not hang the GPU); false on timeout */
+__device__ __forceinline__ bool peer_wait(const int* p, int want) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned ns = 64;
+    while (ld_acquire_sys_s32(p) != want) {
+        __nanosleep(ns); if (ns < 2048) ns <<= 1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > 5000000000ull) return false;
+    }
+    return true;
+}
+
+__global__ void peer_counts_kernel(const PeerArgs P, const int* localTotal) {
+    const int lane = threadIdx.x;
+    PeerPlan* plan = P.plan;
+    const int cnt = __ldcg(localTotal);
+    if (lane == 0) { plan->goalLocal = ~0ull; plan->goalGlobal = ~0ull; }
+    bool ok = true;
+    int c = 0;
+    if (lane < P.world) {
+        PeerMail* m = P.mail[lane] + P.rank;
+        m->count = cnt;
+        __threadfence_system();
+        st_release_sys_s32(&m->seq1, P.seq);
+        const PeerMail* in = P.mail[P.rank] + lane;
+        ok = peer_wait(&in->seq1, P.seq);
+        c = *(volatile const int*)&in->count;
+    }
+    if (__any_sync(0xffffffffu, !ok)) { if (lane == 0) plan->err = 1; return; }
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane < P.world) plan->counts[lane] = c;
+    if (lane == P.rank) plan->base = incl - c;
+    if (lane == 31) plan->total = incl;
+}
+
+/* CTA per scan block: this rank's accepted rows into every rank's tree */
+__global__ void __launch_bounds__(TILE) peer_pack_kernel(const KArgs A, const PeerArgs P, int blkLo, int blkHi, const int* prefix) {
+    __shared__ int sScan[WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DevState* st = A.st;
+    const PeerPlan* plan = P.plan;
+    if (*(volatile const int*)&plan->err) return;
+    const int itr = st->itr, numChunks = st->numChunks, treeSize = st->treeSize, frontierStart = st->frontierStart, children = st->children;
+    const int base = plan->base;
+    const unsigned* chunkMask = A.chunkMask + (size_t)(itr & 1) * A.chunksCap;
+    const float4* stageState = A.stageState + (size_t)(itr & 1) * A.maxCand;
+    const float4* stageCtrl = A.stageCtrl + (size_t)(itr & 1) * A.maxCand;
+    for (int blk = blkLo + (int)blockIdx.x; blk < blkHi; blk += (int)gridDim.x) {
+        const int c = blk * BLK_CHUNKS + tid;
+        const unsigned mask = (c < numChunks) ? __ldcg(&chunkMask[c]) : 0u;
+        const int cnt = __popc(mask);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        __syncthreads();
+        if (lane == 31) sScan[warp] = incl;
+        __syncthreads();
+        int warpBase = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) if (w < warp) warpBase += sScan[w];
+        const int W = __shfl_sync(0xffffffffu, incl, 31);
+        const int c0 = blk * BLK_CHUNKS + warp * 32;
+        const int q0g = base + __ldcg(&prefix[blk - blkLo]) + warpBase;      /* global row index of this warp's first row */
+        for (int q0 = 0; q0 < W; q0 += 32) {
+            const int q = q0 + lane;
+            int i = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int v = __shfl_sync(0xffffffffu, incl, i + step - 1);
+                if (v <= q) i += step;
+            }
+            i = min(i, 31);
+            const unsigned m = __shfl_sync(0xffffffffu, mask, i);
+            const int excl = __shfl_sync(0xffffffffu, incl - cnt, i);
+            if (q < W) {
+                const int r = q - excl;
+                const int bit = nth_set_bit(m, r);
+                const int ci = c0 + i;
+                const int slot = ci * CHUNK + bit;
+                const float4 x = __ldcg(&stageState[ci * CHUNK + r]);
+                const float4 u = __ldcg(&stageCtrl[ci * CHUNK + r]);
+                const int row = q0g + q;
+                const int dst = treeSize + row;
+                const int parent = frontierStart + slot / children;
+                for (int p = 0; p < P.world; ++p) {                            /* updateG on every replica, KGMT.cu:555-591 */
+                    P.treeState[p][dst] = x;
+                    P.treeCtrl[p][dst] = u;
+                    P.treeParent[p][dst] = parent;
+                }
+                if (in_goal(x.x, x.y, A.goalX, A.goalY, A.goalR))
+                    atomicMin(&P.plan->goalLocal, ((unsigned long long)__float_as_uint(u.w) << 32) | (unsigned)row);
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+/* this rank's share [lo, hi) of the delta index space: sum over the ranks, new values into every replica's maps.
+ * delta layout as in shard_apply: R1, R1Valid, R1Invalid, scratch [c1] | R2, R2Valid, R2Invalid, first-reached [c2];
+ * map slab layout: R1, R1Valid, R1Invalid, R1Avail, R1Cov, R1Score x2 [c1] | R2, R2Valid, R2Invalid, R2Stamp [c2] */
+__global__ void peer_reduce_kernel(const KArgs A, const PeerArgs P, size_t c2, size_t lo, size_t hi) {
+    if (*(volatile const int*)&P.plan->err) return;
+    const size_t c1 = (size_t)A.c1;
+    const unsigned stampNew = (unsigned)A.st->itr + 1u;
+    const int* mine = P.mapSlab[P.rank];
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t idx = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < hi; idx += stride) {
+        int sum = 0;
+        for (int p = 0; p < P.world; ++p) sum += __ldcg(&P.delta[p][idx]);
+        if (sum == 0) continue;
+        size_t at; int val; size_t at2 = (size_t)-1; int val2 = 0;
+        if (idx < 4 * c1) {
+            const size_t k = idx / c1, i = idx - k * c1;
+            if (k == 3) continue;                                  /* scratch section */
+            at = k * c1 + i; val = mine[at] + sum;                 /* R1 / R1Valid / R1Invalid */
+            if (k == 1) { at2 = 3 * c1 + i; val2 = 1; }            /* R1Avail, KGMT.cu:400 */
+        } else {
+            const size_t j = idx - 4 * c1, k = j / c2, i = j - k * c2;
+            at = 7 * c1 + k * c2 + i;
+            if (k == 3) { if (mine[at] != 0) continue; val = (int)stampNew; }      /* first reached in this iteration */
+            else val = mine[at] + sum;
+        }
+        for (int p = 0; p < P.world; ++p) {
+            P.mapSlab[p][at] = val;
+            if (at2 != (size_t)-1) P.mapSlab[p][at2] = val2;
+        }
+    }
+    __threadfence_system();
+}
+
+__global__ void peer_barrier_kernel(const PeerArgs P) {
+    const int lane = threadIdx.x;
+    PeerPlan* plan = P.plan;
+    if (*(volatile const int*)&plan->err) return;
+    __threadfence_system();
+    bool ok = true;
+    unsigned long long g = ~0ull;
+    if (lane < P.world) {
+        PeerMail* m = P.mail[lane] + P.rank;
+        m->goal = *(volatile unsigned long long*)&plan->goalLocal;
+        __threadfence_system();
+        st_release_sys_s32(&m->seq2, P.seq);
+        const PeerMail* in = P.mail[P.rank] + lane;
+        ok = peer_wait(&in->seq2, P.seq);
+        g = *(volatile const unsigned long long*)&in->goal;
+    }
+    if (__any_sync(0xffffffffu, !ok)) { if (lane == 0) plan->err = 1; return; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, g, o); g = t < g ? t : g; }
+    if (lane == 0) plan->goalGlobal = g;
+}
+
+__global__ void __launch_bounds__(TILE) peer_finalize_kernel(const KArgs A, const PeerArgs P) {
+    __shared__ float sP[1024];
+    __shared__ DevState S;
+    const int tid = threadIdx.x;
+    DevState* st = A.st;
+    const PeerPlan* plan = P.plan;
+    if (*(volatile const int*)&plan->err) return;
+    if (tid < COPIED_WORDS) reinterpret_cast<int*>(&S)[tid] = __ldcg(reinterpret_cast<const int*>(st) + tid);
+    /* leave this iteration's scan block sums clean (see shard_apply_kernel) */
+    int* bs = A.blockSum + (size_t)(__ldcg(&st->itr) % 3) * A.blocksCap;
+    for (int b = tid; b < A.blocksCap; b += TILE) bs[b] = 0;
+    __syncthreads();
+    const int treeSize0 = S.treeSize;
+    if (tid == 0) {
+        const unsigned long long gb = plan->goalGlobal;          /* (cost bits << 32) | global row: ties break in candidate order */
+        if (gb != ~0ull && S.costToGoal == 0.0f) st->goalIdx = treeSize0 + (int)(unsigned)gb;
+        advance_state(A, S, plan->total, gb);
+    }
+    __syncthreads();
+    if (S.stop == STOP_RUNNING) scores_block(A, sP, A.R1Score[S.itr & 1]);
+    __syncthreads();
+    if (tid < COPIED_WORDS && tid != THRESHOLD_WORD) reinterpret_cast<int*>(st)[tid] = reinterpret_cast<const int*>(&S)[tid];
+    if (tid == 0) { st->scoreReady = S.itr; st->insertDone = S.blocksTotal; }
+}
+
 /* -------------------------------------------- stages 2-4 alone (parity / sweeps) -------
  * candidate s expands parents[s / children] with stream (key0, slot0 + s); writes the
  * candidate records only. */

@@ -40,6 +40,8 @@ ABI_SYMBOLS = [
     "kgmt_dump_csv", "kgmt_tree_size", "kgmt_cost_to_goal", "kgmt_r1_size", "kgmt_r2_size", "kgmt_stream",
     "kgmt_launch_count", "kgmt_get_config", "kgmt_iteration_log",
     "kgmt_set_stream", "kgmt_shard_delta_ints", "kgmt_shard_expand", "kgmt_shard_pack", "kgmt_shard_commit",
+    "kgmt_peer_handle_bytes", "kgmt_peer_export", "kgmt_peer_attach", "kgmt_peer_attach_local", "kgmt_peer_expand_begin",
+    "kgmt_peer_expand_end", "kgmt_peer_detach",
 ]
 
 
@@ -144,6 +146,13 @@ def load():
     L.kgmt_shard_expand.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(ShardInfo)]
     L.kgmt_shard_pack.argtypes = [vp, vp, C.c_int]
     L.kgmt_shard_commit.argtypes = [vp, vp, C.c_int, C.POINTER(C.c_int), C.c_int, vp, C.POINTER(IterStats)]
+    L.kgmt_peer_handle_bytes.restype = C.c_size_t
+    L.kgmt_peer_export.argtypes = [vp, vp, C.c_size_t]
+    L.kgmt_peer_attach.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.kgmt_peer_attach_local.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.kgmt_peer_expand_begin.argtypes = [vp]
+    L.kgmt_peer_expand_end.argtypes = [vp, C.POINTER(IterStats)]
+    L.kgmt_peer_detach.argtypes = [vp]
     _lib = L
     return L
 
@@ -342,6 +351,42 @@ class KGMT:
                                           C.c_void_p(int(delta_ptr)), C.byref(s)))
         self.treeSize_, self.costToGoal_ = s.tree_size, s.cost_to_goal
         return s.as_dict()
+
+    # ------------------------------------------------------------------ sharded expansion over peer memory
+    def peer_export(self):
+        """cudaIpc handles of this planner's tree, maps and exchange block (bytes) for the other ranks."""
+        n = load().kgmt_peer_handle_bytes()
+        buf = (C.c_ubyte * n)()
+        self._ck(load().kgmt_peer_export(self._h, buf, n))
+        return bytes(buf)
+
+    def peer_attach(self, rank, world, all_handles):
+        """all_handles: the peer_export() bytes of every rank, concatenated in rank order."""
+        raw = bytes(all_handles)
+        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        self._ck(load().kgmt_peer_attach(self._h, int(rank), int(world), buf))
+
+    def peer_attach_local(self, rank, planners):
+        """Wire planners living in this process (tests)."""
+        arr = (C.c_void_p * len(planners))(*[p._h for p in planners])
+        self._ck(load().kgmt_peer_attach_local(self._h, int(rank), len(planners), arr))
+
+    def peer_expand_begin(self):
+        self._ck(load().kgmt_peer_expand_begin(self._h))
+
+    def peer_expand_end(self):
+        s = IterStats()
+        self._ck(load().kgmt_peer_expand_end(self._h, C.byref(s)))
+        self.treeSize_, self.costToGoal_ = s.tree_size, s.cost_to_goal
+        return s.as_dict()
+
+    def peer_iterate(self):
+        """One iteration across the attached ranks (every rank calls it)."""
+        self.peer_expand_begin()
+        return self.peer_expand_end()
+
+    def peer_detach(self):
+        self._ck(load().kgmt_peer_detach(self._h))
 
     # ------------------------------------------------------------------ data
     def export(self, array_id):

@@ -113,3 +113,55 @@ class ShardedExpander:
             if st["stop"] != 0:
                 break
         return out
+
+
+class PeerExpander:
+    """The same sharded expansion with the exchange done by the library's own kernels over peer memory (NVLink /
+    NVSwitch): torch.distributed is used ONCE, to gather the cudaIpc handles; no collective on the data path.
+
+    planner: cudasbmp_b200.KGMT (one per process / GPU).  Every rank calls iterate() for the same iteration."""
+
+    def __init__(self, planner, group=None, timing=False):
+        self.p = planner
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        mine = planner.peer_export()
+        if self.world > 1:
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+            allh = torch.empty(self.world * t.numel(), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, t, group=group)
+            handles = bytes(allh.cpu().tolist())
+        else:
+            handles = mine
+        planner.peer_attach(self.rank, self.world, handles)
+        if self.world > 1:
+            dist.barrier(group=group)          # every rank has mapped every other before the first exchange
+        self.timing = timing
+        if timing:
+            planner.set_stream(torch.cuda.current_stream().cuda_stream or 1)
+
+    def iterate(self):
+        if self.timing:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        self.p.peer_expand_begin()
+        if self.timing:
+            e1.record()
+        st = self.p.peer_expand_end()
+        if self.timing:
+            torch.cuda.synchronize()
+            st["total_ms"] = e0.elapsed_time(e1)
+        return st
+
+    def run(self, max_iterations=1 << 30):
+        out = []
+        while len(out) < max_iterations:
+            st = self.iterate()
+            out.append(st)
+            if st["stop"] != 0:
+                break
+        return out
+
+    def close(self):
+        self.p.peer_detach()

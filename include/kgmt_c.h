@@ -188,6 +188,21 @@ int  kgmt_shard_expand(kgmt_ctx* ctx, int rank, int world, int* d_delta, kgmt_sh
 int  kgmt_shard_pack(kgmt_ctx* ctx, void* d_send, int cap_rows);
 int  kgmt_shard_commit(kgmt_ctx* ctx, const void* d_recv, int cap_rows, const int* h_counts, int world, int* d_delta,
                        kgmt_iter_stats* out);
+/* ---- the same sharded expansion with the exchange done by the kernels themselves over PEER MEMORY (NVLink /
+ * NVSwitch), no NCCL on the data path: accepted rows are written straight into every rank's tree, the counter deltas
+ * are all-reduced as reduce-scatter + all-gather over peer loads/stores, counts and the goal candidate travel through
+ * device mailboxes with system-scope release/acquire.  Setup: every rank exports kgmt_peer_handle_bytes() bytes of
+ * cudaIpc handles (kgmt_peer_export), the host program gathers them (any transport) and every rank attaches
+ * (kgmt_peer_attach).  Then one kgmt_peer_expand_begin + kgmt_peer_expand_end per iteration on every rank; results are
+ * bit-identical to kgmt_expand_iteration on one GPU.  A peer that does not arrive within 5 s gives KGMT_ERR_COMM
+ * instead of a hung GPU.  kgmt_peer_attach_local wires contexts of one process (tests). */
+size_t kgmt_peer_handle_bytes(void);
+int  kgmt_peer_export(kgmt_ctx* ctx, void* out_handles, size_t bytes);
+int  kgmt_peer_attach(kgmt_ctx* ctx, int rank, int world, const void* all_handles);
+int  kgmt_peer_attach_local(kgmt_ctx* ctx, int rank, int world, kgmt_ctx* const* peers);
+int  kgmt_peer_expand_begin(kgmt_ctx* ctx);
+int  kgmt_peer_expand_end(kgmt_ctx* ctx, kgmt_iter_stats* out);
+int  kgmt_peer_detach(kgmt_ctx* ctx);
 /* launch on the caller's CUDA stream (cudaStream_t) instead of the context's own; NULL restores it.  Lets the calls
  * above order with NCCL collectives enqueued on the same stream without extra synchronisation. */
 int  kgmt_set_stream(kgmt_ctx* ctx, void* cuda_stream);

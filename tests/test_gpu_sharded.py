@@ -118,3 +118,40 @@ def test_forced_children_sweep_shape():
     assert outs[0][0] == outs[1][0]
     np.testing.assert_array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
     np.testing.assert_array_equal(outs[0][2], outs[1][2])
+
+
+# ---------------------------------------------------------------- peer-memory exchange (no NCCL on the data path)
+@pytest.mark.parametrize("world", [1, 2, 3])
+@pytest.mark.parametrize("cfgname", ["c1", "c2small"])
+def test_peer_memory_iterations_equal_single_gpu(world, cfgname):
+    """kgmt_peer_expand_*: accepted rows written straight into every replica's tree, deltas reduced through peer loads
+    and stores, counts / goal through device mailboxes.  `world` contexts of this process share the GPU and run their
+    exchanges concurrently on their own streams; every replica must equal the single-context run, bit for bit."""
+    if cfgname == "c1":
+        cfg, obs, init, goal = w.C1, w.C1_OBSTACLES, w.C1_INIT, w.C1_GOAL
+    else:
+        cfg, obs, init, goal = dict(w.C2, maxTreeSize=200000), w.c2_obstacles(1000), w.C2_INIT, w.C2_GOAL
+    ref = K.KGMT(**cfg, seed=13); ref.set_obstacles(obs); ref.begin(init, goal)
+    ranks = []
+    for g in range(world):
+        p = K.KGMT(**cfg, seed=13); p.set_obstacles(obs); p.begin(init, goal)
+        ranks.append(p)
+    for g, p in enumerate(ranks):
+        p.peer_attach_local(g, ranks)
+    for it in range(120):
+        want = ref.iterate()
+        for p in ranks:
+            p.peer_expand_begin()
+        got = [p.peer_expand_end() for p in ranks]
+        assert all(g == want for g in got), (it, got[0], want)
+        if it < 6 or want["stop"] != 0:
+            for p in ranks:
+                _same_state(ref, p, want["tree_size"])
+        if want["stop"] != 0:
+            break
+    assert want["stop"] in (1, 2, 3, 4)
+    if want["stop"] == 1:
+        for p in ranks:
+            np.testing.assert_array_equal(ref.extract_path(), p.extract_path())
+    for p in ranks:
+        p.peer_detach()
