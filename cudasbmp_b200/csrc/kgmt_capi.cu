@@ -908,6 +908,15 @@ static int peer_alloc(kgmt_ctx* ctx) {
         CU(cudaMalloc(&ctx->shardTotal, 4));
         CU(cudaHostAlloc(&ctx->hShardTotal, 4, cudaHostAllocDefault));
     }
+    /* load every kernel of the exchange NOW: with lazy module loading the first launch of a kernel uploads its code, and
+     * an upload queued behind a kernel that is spinning on a peer of the SAME device (single-process tests) deadlocks */
+    {
+        cudaFuncAttributes fa;
+        const void* fns[] = {(const void*)shard_reset_kernel, (const void*)shard_entry(ctx->col), (const void*)shard_prefix_kernel,
+                             (const void*)peer_counts_kernel, (const void*)peer_pack_kernel, (const void*)peer_reduce_kernel,
+                             (const void*)peer_barrier_kernel, (const void*)recount_cov_kernel, (const void*)peer_finalize_kernel};
+        for (const void* f : fns) CU(cudaFuncGetAttributes(&fa, f));
+    }
     return KGMT_OK;
 }
 
