@@ -34,7 +34,8 @@ struct kgmt_ctx {
     int* treeParent = nullptr;
     int* mapSlab = nullptr;            /* [R1,R1Valid,R1Invalid,R1Avail,R1Cov,R1Score | R2,R2Valid,R2Invalid,R2Stamp] */
     int* mapSlabCkpt = nullptr;
-    size_t mapSlabInts = 0;
+    size_t mapSlabInts = 0;            /* the region maps (checkpointed, exchanged) */
+    size_t slabInts = 0;               /* + scan / pipeline bookkeeping behind them */
     int *R1 = nullptr, *R1Valid = nullptr, *R1Invalid = nullptr, *R1Avail = nullptr, *R1Cov = nullptr;
     float* R1Score[2] = {nullptr, nullptr};
     int *R2 = nullptr, *R2Valid = nullptr, *R2Invalid = nullptr;
@@ -70,7 +71,7 @@ struct kgmt_ctx {
     float goal[7] = {0};
     long long launches = 0;
     int planLaunches = 0;
-    size_t dirtyTree = 0, dirtyCand = 0;   /* rows a plan may have written since the last clear */
+    size_t dirtyCand = 0;              /* candidate-record rows a plan may have written since the last clear */
     /* batched planning workspaces (kgmt_plan_batch) */
     struct Batch {
         int numWs = 0, clusterSize = 0, Qcap = 0, maxPath = 0;
@@ -364,22 +365,12 @@ static int ensure_record(kgmt_ctx* ctx) {
     return KGMT_OK;
 }
 
-/* state as left by the reference constructor (KGMT.cu:16-40,70-72): zeros, parents -1, scores 1.0.
- * Only the tree / candidate rows a previous plan touched are rewritten (the rest still is in that state).
- * Asynchronous on the context's stream; the scalar block is rebuilt on the host. */
-static int clear_state(kgmt_ctx* ctx, bool sync) {
-    const size_t T = std::min((size_t)ctx->p.max_tree_size, ctx->dirtyTree);
-    if (T) {
-        CU(cudaMemsetAsync(ctx->treeState, 0, T * 16, ctx->stream));
-        CU(cudaMemsetAsync(ctx->treeCtrl, 0, T * 16, ctx->stream));
-        CU(cudaMemsetAsync(ctx->treeParent, 0xFF, T * 4, ctx->stream));
-    }
-    CU(cudaMemsetAsync(ctx->mapSlab, 0, ctx->mapSlabInts * 4, ctx->stream));
-    CU(cudaMemsetAsync(ctx->blockSum, 0, 3 * ctx->blocksCap * 4, ctx->stream));
-    CU(cudaMemsetAsync(ctx->blockDone, 0, 3 * ctx->blocksCap * 4, ctx->stream));
-    CU(cudaMemsetAsync(ctx->blockInserted, 0, 3 * ctx->blocksCap * 4, ctx->stream));
-    CU(cudaMemsetAsync(ctx->pipeCtl, 0, 3 * sizeof(PipeIter), ctx->stream));
-    fill_float_kernel<<<(2 * ctx->c1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->R1Score[0], 1.0f, (size_t)2 * ctx->c1);
+/* state as left by the reference constructor (KGMT.cu:16-40,70-72): maps zero, scores 1.0, no node, no candidate.
+ * Tree rows are NOT rewritten: rows at or above treeSize are dead, and kgmt_export reports them as the constructor
+ * leaves them (zeros, parent -1).  light = the re-plan inside kgmt_plan: one memset of the slab; begin_kernel rebuilds the
+ * scalar block and both score buffers are rewritten before they are read. */
+static int clear_state(kgmt_ctx* ctx, bool sync, bool light = false) {
+    CU(cudaMemsetAsync(ctx->mapSlab, 0, ctx->slabInts * 4, ctx->stream));
     if (ctx->recordAllocated) {
         const size_t M = std::min((size_t)ctx->maxCand, ctx->dirtyCand);
         if (M) {
@@ -391,8 +382,11 @@ static int clear_state(kgmt_ctx* ctx, bool sync) {
             CU(cudaMemsetAsync(ctx->candFlags, 0, M, ctx->stream));
         }
     }
-    ctx->dirtyTree = 0; ctx->dirtyCand = 0;
-    /* scalars: keep the scan epoch monotone across resets */
+    ctx->dirtyCand = 0;
+    ctx->begun = false;
+    ctx->haveCkpt = false;
+    if (light) return KGMT_OK;
+    fill_float_kernel<<<(2 * ctx->c1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->R1Score[0], 1.0f, (size_t)2 * ctx->c1);
     DevState z{};
     z.goalIdx = -1; z.goalSlot = -1; z.goalBest = ~0ull; z.stop = STOP_ITER_LIMIT; z.itr = 1;
     z.forceChildren = ctx->hState->forceChildren;
@@ -402,8 +396,6 @@ static int clear_state(kgmt_ctx* ctx, bool sync) {
         CU(cudaStreamSynchronize(ctx->stream));
         *ctx->hState = z;
     }
-    ctx->begun = false;
-    ctx->haveCkpt = false;
     return KGMT_OK;
 }
 
@@ -424,7 +416,6 @@ static int reset_loop_bookkeeping(kgmt_ctx* ctx) {
 static int fetch_state(kgmt_ctx* ctx) {
     CU(cudaMemcpyAsync(ctx->hState, ctx->dState, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->dirtyTree = std::max(ctx->dirtyTree, (size_t)std::max(ctx->hState->treeSize, 0));
     if (ctx->hState->iterationsDone > 0) ctx->dirtyCand = ctx->maxCand;
     return KGMT_OK;
 }
@@ -480,8 +471,7 @@ void kgmt_destroy(kgmt_ctx* ctx) {
     cudaFree(ctx->mapSlab); cudaFree(ctx->mapSlabCkpt);
     cudaFree(ctx->candState); cudaFree(ctx->candCtrl); cudaFree(ctx->candParent);
     cudaFree(ctx->candR1); cudaFree(ctx->candR2); cudaFree(ctx->candFlags);
-    cudaFree(ctx->chunkMask); cudaFree(ctx->blockSum); cudaFree(ctx->ticket);
-    cudaFree(ctx->blockDone); cudaFree(ctx->blockPrefix); cudaFree(ctx->blockInserted); cudaFree(ctx->pipeCtl);
+    cudaFree(ctx->chunkMask); cudaFree(ctx->ticket); cudaFree(ctx->blockPrefix);
     cudaFree(ctx->stageState); cudaFree(ctx->stageCtrl);
     cudaFree(ctx->dState); cudaFree(ctx->iterLog);
     if (ctx->hState) cudaFreeHost(ctx->hState);
@@ -540,22 +530,24 @@ int kgmt_create(const kgmt_params* p, kgmt_ctx** out) {
     CU(cudaMalloc(&ctx->treeParent, T * 4));
     const size_t c1 = (size_t)ctx->c1, c2 = ctx->c2;
     ctx->mapSlabInts = 7 * c1 + 4 * c2;
-    CU(cudaMalloc(&ctx->mapSlab, ctx->mapSlabInts * 4));
+    ctx->chunksCap = ((size_t)ctx->maxCand + CHUNK - 1) / CHUNK + 1;
+    ctx->blocksCap = (ctx->chunksCap + BLK_CHUNKS - 1) / BLK_CHUNKS + 1;
+    /* one slab: region maps, then the per-iteration scan / pipeline bookkeeping — a re-plan clears all of it with ONE memset */
+    const size_t bookInts = 9 * ctx->blocksCap + 3 * (sizeof(PipeIter) / 4);
+    ctx->slabInts = ((ctx->mapSlabInts + 3) & ~(size_t)3) + bookInts;
+    CU(cudaMalloc(&ctx->mapSlab, ctx->slabInts * 4));
     int* m = ctx->mapSlab;
     ctx->R1 = m; m += c1; ctx->R1Valid = m; m += c1; ctx->R1Invalid = m; m += c1; ctx->R1Avail = m; m += c1;
     ctx->R1Cov = m; m += c1; ctx->R1Score[0] = reinterpret_cast<float*>(m); m += c1;
     ctx->R1Score[1] = reinterpret_cast<float*>(m); m += c1;
     ctx->R2 = m; m += c2; ctx->R2Valid = m; m += c2; ctx->R2Invalid = m; m += c2;
     ctx->R2Stamp = reinterpret_cast<unsigned*>(m);
-    ctx->chunksCap = ((size_t)ctx->maxCand + CHUNK - 1) / CHUNK + 1;
-    ctx->blocksCap = (ctx->chunksCap + BLK_CHUNKS - 1) / BLK_CHUNKS + 1;
+    m = ctx->mapSlab + ((ctx->mapSlabInts + 3) & ~(size_t)3);
+    ctx->blockSum = m; m += 3 * ctx->blocksCap; ctx->blockDone = m; m += 3 * ctx->blocksCap;
+    ctx->blockInserted = m; m += 3 * ctx->blocksCap; ctx->pipeCtl = reinterpret_cast<PipeIter*>(m);
     CU(cudaMalloc(&ctx->chunkMask, 2 * ctx->chunksCap * 4));
-    CU(cudaMalloc(&ctx->blockSum, 3 * ctx->blocksCap * 4));
     CU(cudaMalloc(&ctx->ticket, 4 * 4));
-    CU(cudaMalloc(&ctx->blockDone, 3 * ctx->blocksCap * 4));
     CU(cudaMalloc(&ctx->blockPrefix, 3 * ctx->blocksCap * 4));
-    CU(cudaMalloc(&ctx->blockInserted, 3 * ctx->blocksCap * 4));
-    CU(cudaMalloc(&ctx->pipeCtl, 3 * sizeof(PipeIter)));
     CU(cudaMalloc(&ctx->stageState, 2 * (size_t)ctx->maxCand * 16));
     CU(cudaMalloc(&ctx->stageCtrl, 2 * (size_t)ctx->maxCand * 16));
     CU(cudaMemsetAsync(ctx->chunkMask, 0, 2 * ctx->chunksCap * 4, ctx->stream));
@@ -564,7 +556,7 @@ int kgmt_create(const kgmt_params* p, kgmt_ctx** out) {
     CU(cudaHostAlloc(&ctx->hState, sizeof(DevState), cudaHostAllocDefault));
     memset(ctx->hState, 0, sizeof(DevState));
     if (p->record_candidates) { int rc = ensure_record(ctx); if (rc) return rc; }
-    ctx->dirtyTree = T; ctx->dirtyCand = ctx->maxCand;
+    ctx->dirtyCand = ctx->maxCand;
     int rc = clear_state(ctx, true);
     if (rc) return rc;
     ctx->K = 0; ctx->hObs.clear();
@@ -610,7 +602,7 @@ int kgmt_begin(kgmt_ctx* ctx, const float* initial7, const float* goal7) {
     memcpy(ctx->goal, goal7, sizeof(ctx->goal));
     const KArgs A = make_args(ctx);
     begin_kernel<<<1, TILE, 0, ctx->stream>>>(A, make_float4(initial7[0], initial7[1], initial7[2], initial7[3]),
-                                             make_float4(initial7[4], initial7[5], initial7[6], 0.f));
+                                             make_float4(initial7[4], initial7[5], initial7[6], 0.f), ctx->hState->forceChildren);
     CU(cudaGetLastError());
     ctx->launches += 1;
     ctx->planLaunches = 1;
@@ -666,11 +658,11 @@ int kgmt_plan(kgmt_ctx* ctx, const float* initial7, const float* goal7, kgmt_res
     if (!ctx || !initial7 || !goal7) return fail(ctx, KGMT_ERR_INVALID, "null initial/goal");
     CU(cudaSetDevice(ctx->device));
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (ctx->begun) { int rc = clear_state(ctx, false); if (rc) return rc; }      /* re-plan: inside the timed region */
+    if (ctx->begun) { int rc = clear_state(ctx, false, true); if (rc) return rc; }   /* re-plan: inside the timed region */
     memcpy(ctx->goal, goal7, sizeof(ctx->goal));
     KArgs A = make_args(ctx);
     begin_kernel<<<1, TILE, 0, ctx->stream>>>(A, make_float4(initial7[0], initial7[1], initial7[2], initial7[3]),
-                                             make_float4(initial7[4], initial7[5], initial7[6], 0.f));
+                                             make_float4(initial7[4], initial7[5], initial7[6], 0.f), ctx->hState->forceChildren);
     CU(cudaGetLastError());
     ctx->launches += 1;
     ctx->planLaunches = 1;
@@ -1140,7 +1132,6 @@ int kgmt_seed_frontier(kgmt_ctx* ctx, const float* h_nodes7, int count, const fl
     CU(cudaGetLastError());
     ctx->launches += 4;
     ctx->planLaunches = 4;
-    ctx->dirtyTree = std::max(ctx->dirtyTree, (size_t)count);
     ctx->begun = true;
     return fetch_state(ctx);
 }
@@ -1279,6 +1270,19 @@ int kgmt_export(kgmt_ctx* ctx, int id, void* h_dst, size_t bytes) {
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(h_dst, src, need, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    if (id == KGMT_ARR_SAMPLES || id == KGMT_ARR_PARENT || id == KGMT_ARR_COSTS) {
+        /* tree rows at or above treeSize are dead storage (a re-plan does not rewrite them): report them as the
+         * reference's constructor leaves unused rows — zeros, parent -1 (KGMT.cu:25-26,40) */
+        int rc = fetch_state(ctx);
+        if (rc) return rc;
+        const size_t live = ctx->begun ? (size_t)std::max(ctx->hState->treeSize, 0) : 0;
+        const size_t rows = (size_t)T;
+        if (live < rows) {
+            if (id == KGMT_ARR_SAMPLES) memset((float*)h_dst + live * 7, 0, (rows - live) * 28);
+            else if (id == KGMT_ARR_COSTS) memset((float*)h_dst + live, 0, (rows - live) * 4);
+            else memset((int*)h_dst + live, 0xFF, (rows - live) * 4);
+        }
+    }
     return KGMT_OK;
 }
 

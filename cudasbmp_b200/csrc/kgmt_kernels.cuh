@@ -1398,7 +1398,7 @@ struct BatchArgs {
     size_t c2;
 };
 
-__device__ void begin_block(const KArgs& A, float4 rootState, float4 rootCtrl, float* sP);
+__device__ void begin_block(const KArgs& A, float4 rootState, float4 rootCtrl, float* sP, int forceChildren);
 
 template <int COL>
 __global__ void __launch_bounds__(TILE) batch_kernel(const BatchArgs B) {
@@ -1446,7 +1446,7 @@ __global__ void __launch_bounds__(TILE) batch_kernel(const BatchArgs B) {
         }
         __threadfence();
         grp.sync();
-        if (grp.rank == 0) begin_block(A, B.initState[q], B.initCtrl[q], sPb);
+        if (grp.rank == 0) begin_block(A, B.initState[q], B.initCtrl[q], sPb, 0);
         __threadfence();
         grp.sync();
         run_plan<COL, false, ClusterGroup>(A, 0x7fffffff, grp, cs);
@@ -1972,7 +1972,7 @@ __global__ void __launch_bounds__(TILE) propagate_only_kernel(const KArgs A, con
 
 /* ------------------------------------------------------------------ setup kernels ------ */
 /* root insertion, KGMT.cu:85-114, then the first iteration's shape and scores (one CTA) */
-__device__ void begin_block(const KArgs& A, float4 rootState, float4 rootCtrl, float* sP) {
+__device__ void begin_block(const KArgs& A, float4 rootState, float4 rootCtrl, float* sP, int forceChildren) {
     DevState* st = A.st;
     if (threadIdx.x == 0) {
         A.treeState[0] = rootState;                                                /* :85 */
@@ -1985,7 +1985,7 @@ __device__ void begin_block(const KArgs& A, float4 rootState, float4 rootCtrl, f
         DevState z{};
         z.treeSize = 1; z.frontierStart = 0; z.frontierCount = 1; z.itr = 1;
         z.goalIdx = -1; z.goalSlot = -1; z.costToGoal = 0.0f; z.goalBest = ~0ull;
-        z.forceChildren = st->forceChildren;
+        z.forceChildren = forceChildren;
         A.ticket[0] = A.ticket[1] = A.ticket[2] = A.pipeMode ? 0u : (unsigned)A.totalWarps;
         if (A.pipeMode) for (int r = 0; r < 3; ++r) A.pipe[r] = PipeIter{};
         int stop = STOP_RUNNING;
@@ -2004,9 +2004,9 @@ __device__ void begin_block(const KArgs& A, float4 rootState, float4 rootCtrl, f
     if (threadIdx.x == 0) st_release_s32(&st->scoreReady, 1);
 }
 
-__global__ void __launch_bounds__(TILE) begin_kernel(const KArgs A, float4 rootState, float4 rootCtrl) {
+__global__ void __launch_bounds__(TILE) begin_kernel(const KArgs A, float4 rootState, float4 rootCtrl, int forceChildren) {
     __shared__ float sP[1024];
-    begin_block(A, rootState, rootCtrl, sP);
+    begin_block(A, rootState, rootCtrl, sP, forceChildren);
 }
 
 /* kgmt_seed_frontier: `count` nodes already copied into tree[0,count); all are frontier */
