@@ -255,13 +255,24 @@ __device__ __forceinline__ int block_sum(int v, int* sRed /* [WARPS] */) {
     return t;
 }
 
+/* Ordered insertion of one scan block can be SPLIT over several CTAs (each takes every n-th group of 32 rows): small
+ * iterations have one or two blocks with thousands of accepted rows, and one CTA moving them is a chain of dependent L2
+ * round trips (4-10 us of a 20 us iteration on config 1).  Pure function of the iteration shape, so every CTA agrees. */
+__host__ __device__ __forceinline__ int insert_split(int numBlocks, int groupCtas) {
+    const int s = groupCtas / (numBlocks > 0 ? numBlocks : 1);
+    return s < 1 ? 1 : (s > 8 ? 8 : s);
+}
+
 /* end of an iteration, KGMT.cu:249-259 + the next iteration's :119: pure function of (S, accepted, goalBest),
  * evaluated by thread 0 of EVERY CTA on its own copy. */
 __device__ __forceinline__ void advance_state(const KArgs& A, DevState& S, int accepted, unsigned long long gb) {
     S.lastMode = S.mode; S.lastChildren = S.children; S.lastFrontier = S.frontierCount;
     S.lastM = S.M; S.lastAccepted = accepted; S.lastItr = S.itr;
     S.iterationsDone += 1;
-    S.blocksTotal += (S.numChunks + BLK_CHUNKS - 1) / BLK_CHUNKS;
+    {
+        const int nb = (S.numChunks + BLK_CHUNKS - 1) / BLK_CHUNKS;
+        S.blocksTotal += nb * insert_split(nb, A.totalWarps / WARPS);       /* insertion work items of the iteration */
+    }
     S.expansions += S.M;
     S.frontierStart = S.treeSize;
     S.frontierCount = accepted;
@@ -488,7 +499,8 @@ __device__ __forceinline__ int nth_set_bit(unsigned m, int r) {
  * warp then moves the rows of its 32 chunks with all lanes busy: row q of the warp belongs to
  * the chunk found by a 5-step shuffle search over the inclusive counts.
  * base = accepted candidates in all earlier blocks. */
-__device__ __forceinline__ void insert_block(const KArgs& A, const IterView& it, int blk, int base, int* sScan /* [WARPS] */) {
+__device__ __forceinline__ void insert_block(const KArgs& A, const IterView& it, int blk, int base, int* sScan /* [WARPS] */,
+                                             int slice = 0, int nslices = 1) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blk * BLK_CHUNKS + tid;
     const unsigned mask = (c < it.numChunks) ? __ldcg(&it.chunkMask[c]) : 0u;
@@ -505,7 +517,7 @@ __device__ __forceinline__ void insert_block(const KArgs& A, const IterView& it,
     const int W = __shfl_sync(0xffffffffu, incl, 31);          /* rows of this warp's 32 chunks */
     const int c0 = blk * BLK_CHUNKS + warp * 32;
     const int dst0 = it.treeSize + base + warpBase;
-    for (int q0 = 0; q0 < W; q0 += 32) {
+    for (int q0 = 32 * slice; q0 < W; q0 += 32 * nslices) {
         const int q = q0 + lane;
         int i = 0;                                             /* number of chunks whose inclusive count <= q */
 #pragma unroll
@@ -738,11 +750,13 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
             reinterpret_cast<int*>(st)[tid] = reinterpret_cast<const int*>(&S)[tid];
 
         /* ---- phase B: ordered insertion, scan blocks strided over the CTAs */
-        for (int blk = grp.rank; blk < numBlocks; blk += grp.size) {
+        const int split = insert_split(numBlocks, A.totalWarps / WARPS);
+        for (int v = grp.rank; v < numBlocks * split; v += grp.size) {
+            const int blk = v / split;
             int mine = 0;
             for (int b = tid; b < blk; b += TILE) mine += __ldcg(&it.blockSum[b]);
             const int base = block_sum(mine, sRed);
-            insert_block(A, it, blk, base, sRed);
+            insert_block(A, it, blk, base, sRed, v - blk * split, split);
         }
         stamp(5);
     }
