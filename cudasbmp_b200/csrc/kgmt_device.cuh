@@ -167,7 +167,8 @@ __device__ __forceinline__ bool propagate_edge(float4& s, const Controls& u, con
     bool valid = true;
     for (int i = 0; i < p.numDisc; ++i) {
         const float px = x, py = y;
-        const float sn = sinf(th), cs = cosf(th);
+        float sn, cs;
+        sincosf(th, &sn, &cs);      /* one range reduction; bit-identical to sinf(th), cosf(th) (checked against the reference's kernels) */
         x = __fmaf_rn(dt, __fmul_rn(v, cs), x);
         y = __fmaf_rn(dt, __fmul_rn(v, sn), y);
         if (x <= 0.0f || x >= p.W || y <= 0.0f || y >= p.H) { valid = false; break; }
@@ -200,7 +201,8 @@ __device__ __forceinline__ void edge_tile_pass(const float4 s0, const Controls& 
     const int limit = FIRST ? p.numDisc : e.step;
     for (int i = 0; i < limit; ++i) {
         const float px = x, py = y;
-        const float sn = sinf(th), cs = cosf(th);
+        float sn, cs;
+        sincosf(th, &sn, &cs);      /* one range reduction; bit-identical to sinf(th), cosf(th) (checked against the reference's kernels) */
         x = __fmaf_rn(dt, __fmul_rn(v, cs), x);
         y = __fmaf_rn(dt, __fmul_rn(v, sn), y);
         if (FIRST && (x <= 0.0f || x >= p.W || y <= 0.0f || y >= p.H)) {            /* :42-45 */
