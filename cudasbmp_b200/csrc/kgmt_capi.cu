@@ -280,10 +280,12 @@ static int build_cull_grid(kgmt_ctx* ctx) {
     }
     for (size_t i = 0; i < (size_t)C * C; ++i) start[i + 1] += start[i];
     const int realItems = start[(size_t)C * C];
-    const int numItems = realItems + 1;          /* + one box nothing overlaps: the cell walk may read one entry past a list */
+    const int numItems = realItems + 3;          /* + three boxes nothing overlaps: the cell walk reads four entries per trip */
     std::vector<float> items((size_t)numItems * 4, 0.0f);
-    items[(size_t)realItems * 4] = INFINITY; items[(size_t)realItems * 4 + 1] = INFINITY;
-    items[(size_t)realItems * 4 + 2] = -INFINITY; items[(size_t)realItems * 4 + 3] = -INFINITY;
+    for (int k = realItems; k < numItems; ++k) {
+        items[(size_t)k * 4] = INFINITY; items[(size_t)k * 4 + 1] = INFINITY;
+        items[(size_t)k * 4 + 2] = -INFINITY; items[(size_t)k * 4 + 3] = -INFINITY;
+    }
     std::vector<int> fill(start.begin(), start.end() - 1);
     for (int k = 0; k < K; ++k) {
         const int x0 = cull_cell(o[4 * k], invX, C), x1 = cull_cell(o[4 * k + 2], invX, C);

@@ -138,10 +138,13 @@ struct CollideGrid {
             const int row = cy * C;
             const int e = cellStart[row + cx1 + 1];
             int k = cellStart[row + cx0];
-            /* two items per trip: the list ends with one never-overlapping entry, so items[k + 1] is always readable */
-            for (; k < e && !h; k += 2) {
-                const float4 o0 = items[k], o1 = items[k + 1];
-                h = aabb_overlap(bnx, bny, bxx, bxy, o0) | ((k + 1 < e) & aabb_overlap(bnx, bny, bxx, bxy, o1));
+            /* four items per trip, read unconditionally: an entry past the end of this row's range is another cell's
+             * obstacle (or one of the three never-overlapping entries that close the array), and a box that overlaps
+             * the step bbox is a collision whichever cell it was filed under — over-reading cannot change the flag */
+            for (; k < e && !h; k += 4) {
+                const float4 o0 = items[k], o1 = items[k + 1], o2 = items[k + 2], o3 = items[k + 3];
+                h = aabb_overlap(bnx, bny, bxx, bxy, o0) | aabb_overlap(bnx, bny, bxx, bxy, o1) |
+                    aabb_overlap(bnx, bny, bxx, bxy, o2) | aabb_overlap(bnx, bny, bxx, bxy, o3);
             }
         }
         return h;
