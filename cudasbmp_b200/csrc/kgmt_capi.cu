@@ -67,6 +67,7 @@ struct kgmt_ctx {
     int col = COL_GRID_SMEM; size_t smemBytes = 0; int useHist = 0;
     int gridLoop = 0, gridMax = 0;
     bool configured = false;
+    int cfgCol = -1, cfgPipe = -1; size_t cfgSmem = 0;      /* what the launch configuration was resolved for */
     bool begun = false;
     float goal[7] = {0};
     long long launches = 0;
@@ -222,6 +223,10 @@ static int configure(kgmt_ctx* ctx) {
         if (want == 0) { const char* e = getenv("KGMT_PIPE"); want = e ? (atoi(e) ? 1 : 2) : KGMT_DEFAULT_LOOP; }
         ctx->pipe = (want == 1 && col != COL_BRUTE_STREAM) ? 1 : 0;
     }
+    /* a new obstacle set of the same size class resolves to the same kernels and shared-memory size: keep the launch
+     * configuration (the attribute / occupancy queries below are ~100 us of driver calls per kgmt_set_obstacles) */
+    if (ctx->configured && ctx->cfgCol == col && ctx->cfgSmem == ctx->smemBytes && ctx->cfgPipe == ctx->pipe) return KGMT_OK;
+    ctx->cfgCol = col; ctx->cfgSmem = ctx->smemBytes; ctx->cfgPipe = ctx->pipe;
     int occ = 1 << 30;
     for (int rec = 0; rec < 2; ++rec) {
         expand_fn f = ctx->pipe ? pipe_entry(col, rec != 0) : expand_entry(col, rec != 0);
