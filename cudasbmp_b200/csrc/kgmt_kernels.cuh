@@ -27,6 +27,11 @@
  *            chunk waits (acquire) only for the 256-row tree segment holding its
  *            parent and for the score buffer of its iteration.
  *
+ * Also in this file: run_plan_pipe (the same loop without a grid barrier — experimental, see its header),
+ * batch_kernel (one thread-block cluster per query, config 4), shard_* (one iteration split over ranks, NCCL
+ * exchange by the caller) and peer_* (the same with the exchange done over peer memory), propagate_only_kernel
+ * (stages 2-4 alone), setup / export kernels.
+ *
  * Canonical semantics where the reference races: SURVEY.md Appendix B.
  */
 #pragma once
