@@ -47,6 +47,7 @@ struct kgmt_ctx {
     unsigned* chunkMask = nullptr; int* blockSum = nullptr; unsigned* ticket = nullptr;
     int* blockDone = nullptr; int* blockPrefix = nullptr; int* blockInserted = nullptr; PipeIter* pipeCtl = nullptr;   /* pipelined loop */
     int pipe = 0;                      /* 1: kgmt_plan / kgmt_expand_iterations run the barrier-free loop (run_plan_pipe) */
+    int raceId = 0;                    /* > 0 while kgmt_peer_race runs */
     size_t chunksCap = 0, blocksCap = 0;
     float4 *stageState = nullptr, *stageCtrl = nullptr;
     unsigned long long* iterLog = nullptr;
@@ -90,7 +91,8 @@ struct kgmt_ctx {
     /* sharded expansion over peer memory (kgmt_peer_*) */
     struct Peer {
         int rank = -1, world = 0, seq = 0; bool ipc = false, inFlight = false;
-        unsigned char* block = nullptr; size_t blockBytes = 0, mailOff = 0;     /* [delta slab | mailbox[PEER_MAX]] */
+        unsigned char* block = nullptr; size_t blockBytes = 0, mailOff = 0, raceOff = 0;   /* [delta slab | mailbox[PEER_MAX] | race flag] */
+        int** dRaceFlags = nullptr;                                              /* device table of every rank's race flag */
         PeerPlan* plan = nullptr; PeerPlan* hPlan = nullptr;                    /* device, pinned host */
         void* opened[PEER_MAX][5] = {};                                          /* cudaIpcOpenMemHandle results to close */
         PeerArgs args{};
@@ -183,6 +185,7 @@ static KArgs make_args(const kgmt_ctx* c) {
     A.stageState = c->stageState; A.stageCtrl = c->stageCtrl;
     A.chunksCap = (int)c->chunksCap; A.blocksCap = (int)c->blocksCap; A.maxCand = c->maxCand; A.totalWarps = c->gridLoop * WARPS;
     A.blockDone = c->blockDone; A.blockPrefix = c->blockPrefix; A.blockInserted = c->blockInserted; A.pipe = c->pipeCtl; A.pipeMode = c->pipe;
+    A.raceId = c->raceId; A.raceWorld = c->peer.world; A.raceRank = c->peer.rank; A.raceFlags = c->peer.dRaceFlags;
     A.st = c->dState;
     A.obstacles = c->dObs; A.K = c->K;
     A.cellStart = c->dCellStart; A.cellItems = c->dCellItems; A.cullC = c->cullC;
@@ -488,7 +491,7 @@ void kgmt_destroy(kgmt_ctx* ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
-    cudaFree(ctx->peer.block); cudaFree(ctx->peer.plan);
+    cudaFree(ctx->peer.block); cudaFree(ctx->peer.plan); cudaFree(ctx->peer.dRaceFlags);
     if (ctx->peer.hPlan) cudaFreeHost(ctx->peer.hPlan);
     cudaFree(ctx->shardPrefix); cudaFree(ctx->shardTotal);
     if (ctx->hShardTotal) cudaFreeHost(ctx->hShardTotal);
@@ -896,7 +899,9 @@ static int peer_alloc(kgmt_ctx* ctx) {
     if (pr.block) return KGMT_OK;
     const size_t deltaBytes = kgmt_shard_delta_ints(ctx) * 4;
     pr.mailOff = (deltaBytes + 255) & ~(size_t)255;
-    pr.blockBytes = std::max<size_t>(pr.mailOff + PEER_MAX * sizeof(PeerMail), (size_t)2 << 20);   /* its own allocation granule */
+    pr.raceOff = (pr.mailOff + PEER_MAX * sizeof(PeerMail) + 255) & ~(size_t)255;
+    pr.blockBytes = std::max<size_t>(pr.raceOff + 256, (size_t)2 << 20);   /* its own allocation granule */
+    CU(cudaMalloc(&pr.dRaceFlags, PEER_MAX * sizeof(int*)));
     CU(cudaMalloc(&pr.block, pr.blockBytes));
     CU(cudaMemset(pr.block, 0, pr.blockBytes));
     CU(cudaMalloc(&pr.plan, sizeof(PeerPlan)));
@@ -933,6 +938,13 @@ int kgmt_peer_export(kgmt_ctx* ctx, void* out_handles, size_t bytes) {
     CU(cudaIpcGetMemHandle(&h[2], ctx->treeParent));
     CU(cudaIpcGetMemHandle(&h[3], ctx->mapSlab));
     CU(cudaIpcGetMemHandle(&h[4], ctx->peer.block));
+    return KGMT_OK;
+}
+
+static int peer_publish_tables(kgmt_ctx* ctx) {
+    int* flags[PEER_MAX] = {};
+    for (int p = 0; p < ctx->peer.world; ++p) flags[p] = (int*)((unsigned char*)ctx->peer.args.delta[p] + ctx->peer.raceOff);
+    CU(cudaMemcpy(ctx->peer.dRaceFlags, flags, sizeof(flags), cudaMemcpyHostToDevice));
     return KGMT_OK;
 }
 
@@ -977,7 +989,7 @@ int kgmt_peer_attach(kgmt_ctx* ctx, int rank, int world, const void* all_handles
     }
     pr.rank = rank; pr.world = world; pr.seq = 0; pr.ipc = true;
     pr.args.rank = rank; pr.args.world = world; pr.args.plan = pr.plan;
-    return KGMT_OK;
+    return peer_publish_tables(ctx);
 }
 
 /* the same wiring between contexts of ONE process (tests; several contexts may share a device) */
@@ -1008,7 +1020,21 @@ int kgmt_peer_attach_local(kgmt_ctx* ctx, int rank, int world, kgmt_ctx* const* 
     }
     pr.rank = rank; pr.world = world; pr.seq = 0; pr.ipc = false;
     pr.args.rank = rank; pr.args.world = world; pr.args.plan = pr.plan;
-    return KGMT_OK;
+    return peer_publish_tables(ctx);
+}
+
+/* Portfolio race (first-solution termination over peer memory): every attached rank plans the SAME query with its own
+ * seed in its usual single cooperative launch; the rank that reaches the goal first writes race_id into every peer's
+ * race word (system-scope release over NVLink) and the others stop at their next iteration with KGMT_PEER_SOLVED.
+ * race_id must be > 0 and grow from race to race.  No collective, no host round trip inside the race. */
+int kgmt_peer_race(kgmt_ctx* ctx, const float* initial7, const float* goal7, int race_id, kgmt_result* out) {
+    if (!ctx || race_id <= 0) return fail(ctx, KGMT_ERR_INVALID, "race_id must be positive");
+    if (ctx->peer.rank < 0) return fail(ctx, KGMT_ERR_STATE, "kgmt_peer_race before kgmt_peer_attach");
+    if (ctx->pipe) return fail(ctx, KGMT_ERR_STATE, "kgmt_peer_race needs the grid-barrier loop (params.reserved[2] = 2)");
+    ctx->raceId = race_id;
+    const int rc = kgmt_plan(ctx, initial7, goal7, out);
+    ctx->raceId = 0;
+    return rc;
 }
 
 /* enqueue ONE expansion iteration across the attached ranks (every rank must call it for the same iteration) */

@@ -50,7 +50,8 @@ constexpr int WARPS = TILE / 32;
 constexpr int CHUNK = 32;                 /* candidates per chunk == one warp */
 constexpr int BLK_CHUNKS = 256;           /* chunks per scan block (one per thread of a CTA in phase B) */
 
-enum { STOP_RUNNING = 0, STOP_SOLVED = 1, STOP_TREE_FULL = 2, STOP_ITER_LIMIT = 3, STOP_FRONTIER_EMPTY = 4 };
+enum { STOP_RUNNING = 0, STOP_SOLVED = 1, STOP_TREE_FULL = 2, STOP_ITER_LIMIT = 3, STOP_FRONTIER_EMPTY = 4,
+       STOP_PEER_SOLVED = 5 /* portfolio race: another GPU reached the goal first */ };
 enum { COL_GRID_SMEM = 0, COL_GRID_GLOBAL = 1, COL_BRUTE_SMEM = 2, COL_BRUTE_GLOBAL = 3, COL_BRUTE_STREAM = 4 };
 constexpr int STREAM_TILE = 1024;         /* obstacles per streamed shared-memory tile (16 KB), double buffered */
 enum { FLAG_VALID = 1, FLAG_ACCEPT = 2 };
@@ -71,6 +72,8 @@ struct DevState {
     int scoreReady;                                             /* scores of this iteration are complete (release/acquire) */
     int insertDone;                                             /* scan blocks inserted so far, whole plan (release counter) */
     int pipeEpoch;                                              /* pipelined loop: iterations finalized and published so far */
+    int peerSolved;                                             /* portfolio race: a peer's win as seen before this iteration's barrier */
+    int pad2;
 };
 constexpr int COPIED_WORDS = 24;
 constexpr int THRESHOLD_WORD = 7;         /* R1Threshold: written by scores_block straight to global memory, never copied back */
@@ -113,6 +116,9 @@ struct KArgs {
     int* blockInserted;           /* [3][blocksCap] insertion units of the block whose rows are in the tree */
     struct PipeIter* pipe;        /* [3] */
     int pipeMode;                 /* 1: tickets start at 0 (run_plan_pipe), 0: at totalWarps (run_plan) */
+    /* portfolio race over peer memory (kgmt_peer_race): raceId > 0 switches it on */
+    int raceId, raceWorld, raceRank;
+    int* const* raceFlags;        /* device table [raceWorld]: every rank's 'a plan of race N was solved' word, mapped here */
     DevState* st;
     /* collision */
     const float4* obstacles; int K;
@@ -239,6 +245,14 @@ __device__ __forceinline__ int ld_relaxed_s32(const int* p) {
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_release_sys_s32(int* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys_s32(const int* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 /* wait until *p >= want: relaxed polling with back-off, one acquire fence at the end */
 __device__ __forceinline__ void wait_ge(const int* p, int want) {
@@ -270,7 +284,7 @@ __host__ __device__ __forceinline__ int insert_split(int numBlocks, int groupCta
 
 /* end of an iteration, KGMT.cu:249-259 + the next iteration's :119: pure function of (S, accepted, goalBest),
  * evaluated by thread 0 of EVERY CTA on its own copy. */
-__device__ __forceinline__ void advance_state(const KArgs& A, DevState& S, int accepted, unsigned long long gb) {
+__device__ __forceinline__ void advance_state(const KArgs& A, DevState& S, int accepted, unsigned long long gb, int peerSolved = 0) {
     S.lastMode = S.mode; S.lastChildren = S.children; S.lastFrontier = S.frontierCount;
     S.lastM = S.M; S.lastAccepted = accepted; S.lastItr = S.itr;
     S.iterationsDone += 1;
@@ -291,6 +305,7 @@ __device__ __forceinline__ void advance_state(const KArgs& A, DevState& S, int a
     else if (S.treeSize >= A.maxTree)      stop = STOP_TREE_FULL;                   /* :255 */
     else if (accepted == 0)                stop = STOP_FRONTIER_EMPTY;
     else if (S.itr >= A.numIterations)     stop = STOP_ITER_LIMIT;                  /* :118 */
+    else if (peerSolved)                   stop = STOP_PEER_SOLVED;
     S.stop = stop;
     if (stop == STOP_RUNNING) {
         S.itr += 1;                                                                 /* :119 */
@@ -712,6 +727,10 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
             }
         }
         stamp(3);
+        /* portfolio race: ONE thread looks at the 'a peer has solved' word before the barrier, so that every CTA takes the
+         * same decision after it */
+        if (A.raceId > 0 && grp.rank == 0 && tid == 0)
+            st->peerSolved = (ld_acquire_sys_s32(A.raceFlags[A.raceRank]) == A.raceId) ? 1 : 0;
         grp.sync();                    /* the one barrier: all ballots, block sums, maps and the goal minimum are final */
         stamp(4);
 
@@ -724,8 +743,13 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
             if (tid == 0) {
                 sGoalBest = *(volatile unsigned long long*)&st->goalBest;
                 const bool hadGoal = S.costToGoal != 0.0f;
-                advance_state(A, S, accepted, sGoalBest);
+                advance_state(A, S, accepted, sGoalBest, A.raceId > 0 ? *(volatile int*)&st->peerSolved : 0);
                 sAccepted = (!hadGoal && S.costToGoal != 0.0f) ? S.goalSlot : -1;
+                if (A.raceId > 0 && grp.rank == 0 && S.stop == STOP_SOLVED) {
+                    /* first solution: tell every other GPU of the race (system-scope release over NVLink) */
+                    for (int p = 0; p < A.raceWorld; ++p)
+                        if (p != A.raceRank) st_release_sys_s32(A.raceFlags[p], A.raceId);
+                }
                 if (grp.rank == 0 && A.iterLog && logRow < 255) {
                     unsigned long long t;
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -1740,14 +1764,6 @@ struct PeerArgs {
     PeerPlan* plan;                                                             /* local */
 };
 
-__device__ __forceinline__ void st_release_sys_s32(int* p, int v) {
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_acquire_sys_s32(const int* p) {
-    int v;
-    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 /* wait until *p == want, at most ~5 s (a peer that never arrives must not hang the GPU); false on timeout */
 __device__ __forceinline__ bool peer_wait(const int* p, int want) {
     unsigned long long t0, t;

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkgmt_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM, ERR_COMM = 0, -1, -2, -3, -4, -5
-STOP = {0: "running", 1: "solved", 2: "tree_full", 3: "iter_limit", 4: "frontier_empty"}
+STOP = {0: "running", 1: "solved", 2: "tree_full", 3: "iter_limit", 4: "frontier_empty", 5: "peer_solved"}
 COLLIDE_GRID, COLLIDE_BRUTE = 0, 1
 
 (ARR_SAMPLES, ARR_UNEXPLORED, ARR_PARENT, ARR_U_PARENT, ARR_G, ARR_R2AVAIL, ARR_R1AVAIL, ARR_R1VALID, ARR_R2VALID,
@@ -41,7 +41,7 @@ ABI_SYMBOLS = [
     "kgmt_launch_count", "kgmt_get_config", "kgmt_iteration_log",
     "kgmt_set_stream", "kgmt_shard_delta_ints", "kgmt_shard_expand", "kgmt_shard_pack", "kgmt_shard_commit",
     "kgmt_peer_handle_bytes", "kgmt_peer_export", "kgmt_peer_attach", "kgmt_peer_attach_local", "kgmt_peer_expand_begin",
-    "kgmt_peer_expand_end", "kgmt_peer_detach",
+    "kgmt_peer_expand_end", "kgmt_peer_detach", "kgmt_peer_race",
 ]
 
 
@@ -153,6 +153,7 @@ def load():
     L.kgmt_peer_expand_begin.argtypes = [vp]
     L.kgmt_peer_expand_end.argtypes = [vp, C.POINTER(IterStats)]
     L.kgmt_peer_detach.argtypes = [vp]
+    L.kgmt_peer_race.argtypes = [vp, f32p, f32p, C.c_int, C.POINTER(Result)]
     _lib = L
     return L
 
@@ -384,6 +385,16 @@ class KGMT:
         """One iteration across the attached ranks (every rank calls it)."""
         self.peer_expand_begin()
         return self.peer_expand_end()
+
+    def peer_race(self, initial, goal, race_id):
+        """Portfolio race with the attached ranks: this rank's plan of the query (its own seed), stopped early with
+        stop == 5 when another rank reaches the goal first."""
+        i, g = _f32(initial, 7), _f32(goal, 7)
+        r = Result()
+        f32p = C.POINTER(C.c_float)
+        self._ck(load().kgmt_peer_race(self._h, i.ctypes.data_as(f32p), g.ctypes.data_as(f32p), int(race_id), C.byref(r)))
+        self.treeSize_, self.costToGoal_ = r.tree_size, r.cost_to_goal
+        return r.as_dict()
 
     def peer_detach(self):
         self._ck(load().kgmt_peer_detach(self._h))

@@ -43,7 +43,8 @@ typedef enum kgmt_stop {
     KGMT_SOLVED = 1,                 /* costToGoal != 0                      KGMT.cu:252 */
     KGMT_TREE_FULL = 2,              /* treeSize >= maxTreeSize              KGMT.cu:255 */
     KGMT_ITER_LIMIT = 3,             /* itr == numIterations                 KGMT.cu:118 */
-    KGMT_FRONTIER_EMPTY = 4          /* nothing accepted: the reference spins to numIterations */
+    KGMT_FRONTIER_EMPTY = 4,         /* nothing accepted: the reference spins to numIterations */
+    KGMT_PEER_SOLVED = 5             /* kgmt_peer_race: another GPU of the race reached the goal first */
 } kgmt_stop;
 
 typedef enum kgmt_collide {
@@ -203,6 +204,10 @@ int  kgmt_peer_attach_local(kgmt_ctx* ctx, int rank, int world, kgmt_ctx* const*
 int  kgmt_peer_expand_begin(kgmt_ctx* ctx);
 int  kgmt_peer_expand_end(kgmt_ctx* ctx, kgmt_iter_stats* out);
 int  kgmt_peer_detach(kgmt_ctx* ctx);
+/* portfolio race between the attached ranks: same query, own seed per rank (kgmt_set_seed), ONE launch per rank; the
+ * first rank to reach the goal stops the others through a word in their memory; they return KGMT_PEER_SOLVED.
+ * race_id > 0, growing from race to race (KGMT::plan has no counterpart: KGMT.cu:118-259 is a single-GPU loop). */
+int  kgmt_peer_race(kgmt_ctx* ctx, const float* initial7, const float* goal7, int race_id, kgmt_result* out);
 /* launch on the caller's CUDA stream (cudaStream_t) instead of the context's own; NULL restores it.  Lets the calls
  * above order with NCCL collectives enqueued on the same stream without extra synchronisation. */
 int  kgmt_set_stream(kgmt_ctx* ctx, void* cuda_stream);

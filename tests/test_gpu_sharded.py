@@ -155,3 +155,26 @@ def test_peer_memory_iterations_equal_single_gpu(world, cfgname):
             np.testing.assert_array_equal(ref.extract_path(), p.extract_path())
     for p in ranks:
         p.peer_detach()
+
+
+def test_peer_portfolio_race_flag():
+    """kgmt_peer_race: the rank that reaches the goal tells the others through a word in their memory; a rank that finds
+    the word set for the current race stops at its next iteration boundary with stop == 5 (peer solved).  Two contexts of
+    this process take turns (two cooperative launches cannot share one GPU), which makes the outcome deterministic."""
+    cfg, obs = w.C1, w.C1_OBSTACLES
+    a = K.KGMT(**cfg, seed=3); a.set_obstacles(obs)
+    b = K.KGMT(**cfg, seed=4); b.set_obstacles(obs)
+    ref = K.KGMT(**cfg, seed=3); ref.set_obstacles(obs)
+    want = ref.plan(w.C1_INIT, w.C1_GOAL)
+    a.peer_attach_local(0, [a, b]); b.peer_attach_local(1, [a, b])
+    ra = a.peer_race(w.C1_INIT, w.C1_GOAL, race_id=1)
+    assert ra["stop"] == 1 and (ra["tree_size"], ra["iterations"], ra["cost_to_goal"]) == (want["tree_size"], want["iterations"], want["cost_to_goal"])
+    rb = b.peer_race(w.C1_INIT, w.C1_GOAL, race_id=1)               # a has already won race 1
+    assert rb["stop"] == 5 and rb["iterations"] == 1
+    rb2 = b.peer_race(w.C1_INIT, w.C1_GOAL, race_id=2)              # a new race: nobody has solved it yet
+    assert rb2["stop"] == 1 and rb2["iterations"] > 1
+    ra2 = a.peer_race(w.C1_INIT, w.C1_GOAL, race_id=2)              # ... and now b has
+    assert ra2["stop"] == 5
+    # an ordinary plan ignores the race words
+    assert a.plan(w.C1_INIT, w.C1_GOAL)["stop"] == 1
+    a.peer_detach(); b.peer_detach()
