@@ -1394,8 +1394,16 @@ __device__ void run_plan_pipe(const KArgs& A, int maxIters, const ColSet& cs) {
 #endif
 }
 
+#ifndef KGMT_EXPAND_MIN_CTAS
+#define KGMT_EXPAND_MIN_CTAS 3        /* register budget of the cooperative kernel: 65536 / (256 * 3) = 85 per thread */
+#endif
+#ifdef KGMT_EXPAND_MAXNREG
+#define KGMT_EXPAND_BOUNDS __maxnreg__(KGMT_EXPAND_MAXNREG)
+#else
+#define KGMT_EXPAND_BOUNDS __launch_bounds__(TILE, KGMT_EXPAND_MIN_CTAS)
+#endif
 template <int COL, bool RECORD>
-__global__ void __launch_bounds__(TILE) expand_kernel(const KArgs A, int maxIters) {
+__global__ void KGMT_EXPAND_BOUNDS expand_kernel(const KArgs A, int maxIters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t sBar;
     GridGroup grp;
@@ -1443,8 +1451,11 @@ struct BatchArgs {
 
 __device__ void begin_block(const KArgs& A, float4 rootState, float4 rootCtrl, float* sP, int forceChildren);
 
+#ifndef KGMT_BATCH_MIN_CTAS
+#define KGMT_BATCH_MIN_CTAS 4         /* many small trees: occupancy (concurrent workspaces) matters more than registers */
+#endif
 template <int COL>
-__global__ void __launch_bounds__(TILE) batch_kernel(const BatchArgs B) {
+__global__ void __launch_bounds__(TILE, KGMT_BATCH_MIN_CTAS) batch_kernel(const BatchArgs B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t sBar;
     __shared__ float sPb[1024];
