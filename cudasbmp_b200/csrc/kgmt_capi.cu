@@ -1056,6 +1056,7 @@ int kgmt_peer_expand_begin(kgmt_ctx* ctx) {
     cudaStream_t st = ctx->stream;
     pr.seq += 1;
     pr.args.seq = pr.seq;
+    CU(cudaMemsetAsync(pr.plan, 0, sizeof(PeerPlan), st));      /* also clears the error flag of a timed-out exchange */
     const KArgs As = make_shard_args(ctx, (int*)pr.block);
     const KArgs A = make_args(ctx);
     const int grid = std::max(1, std::min(ctx->shardGrid, (chunks + WARPS - 1) / WARPS));

@@ -196,7 +196,8 @@ int  kgmt_shard_commit(kgmt_ctx* ctx, const void* d_recv, int cap_rows, const in
  * cudaIpc handles (kgmt_peer_export), the host program gathers them (any transport) and every rank attaches
  * (kgmt_peer_attach).  Then one kgmt_peer_expand_begin + kgmt_peer_expand_end per iteration on every rank; results are
  * bit-identical to kgmt_expand_iteration on one GPU.  A peer that does not arrive within 5 s gives KGMT_ERR_COMM
- * instead of a hung GPU.  kgmt_peer_attach_local wires contexts of one process (tests). */
+ * instead of a hung GPU; the replicas of an aborted exchange are undefined — restart the plan (kgmt_begin) on every
+ * rank.  kgmt_peer_attach_local wires contexts of one process (tests). */
 size_t kgmt_peer_handle_bytes(void);
 int  kgmt_peer_export(kgmt_ctx* ctx, void* out_handles, size_t bytes);
 int  kgmt_peer_attach(kgmt_ctx* ctx, int rank, int world, const void* all_handles);

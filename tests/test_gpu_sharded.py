@@ -178,3 +178,37 @@ def test_peer_portfolio_race_flag():
     # an ordinary plan ignores the race words
     assert a.plan(w.C1_INIT, w.C1_GOAL)["stop"] == 1
     a.peer_detach(); b.peer_detach()
+
+
+def test_peer_exchange_times_out_instead_of_hanging():
+    """A rank whose peer never arrives gets KGMT_ERR_COMM after ~5 s — the spin-wait kernels give up instead of hanging
+    the GPU.  The replicas of an aborted exchange are undefined (rows and counters may be partly applied); after a fresh
+    kgmt_begin on every rank the exchange works again."""
+    import time
+    cfg, obs = dict(w.C1, maxTreeSize=4000), w.C1_OBSTACLES
+    ranks = []
+    for g in range(2):
+        p = K.KGMT(**cfg, seed=21); p.set_obstacles(obs); p.begin(w.C1_INIT, w.C1_GOAL)
+        ranks.append(p)
+    ref = K.KGMT(**cfg, seed=21); ref.set_obstacles(obs); ref.begin(w.C1_INIT, w.C1_GOAL)
+    for g, p in enumerate(ranks):
+        p.peer_attach_local(g, ranks)
+    t0 = time.perf_counter()
+    ranks[0].peer_expand_begin()                      # rank 1 does not take part
+    with pytest.raises(K.KgmtError, match="did not arrive"):
+        ranks[0].peer_expand_end()
+    assert 4.0 < time.perf_counter() - t0 < 20.0
+    ranks[1].peer_expand_begin()                      # rank 1 catches up with the exchange counter: its partner is gone
+    with pytest.raises(K.KgmtError):
+        ranks[1].peer_expand_end()
+    for p in ranks:
+        p.begin(w.C1_INIT, w.C1_GOAL)                 # restart the plan on every replica
+    for it in range(3):
+        want = ref.iterate()
+        for p in ranks:
+            p.peer_expand_begin()
+        got = [p.peer_expand_end() for p in ranks]
+        assert all(g == want for g in got), (it, got, want)
+    for p in ranks:
+        _same_state(ref, p, want["tree_size"])
+        p.peer_detach()
