@@ -212,3 +212,37 @@ def test_peer_exchange_times_out_instead_of_hanging():
     for p in ranks:
         _same_state(ref, p, want["tree_size"])
         p.peer_detach()
+
+
+def test_c5_full_size_one_iteration_property():
+    """BASELINE config 5 at its largest size: ONE iteration of 2^26 candidates (32 768 seeded parents x 2 048 children,
+    config-2 map).  The cooperative kernel and the sharded sequence (peer-memory path, one rank) must agree on every
+    region counter, on the accepted count and on every parent link; counters must add up to the candidates."""
+    obs = w.c2_obstacles(1000)
+    P, M = 32768, 1 << 26
+    parents = w.random_parents(P, obs, seed=7)
+    cfg = dict(w.C1, maxTreeSize=M + P, numIterations=2)
+    out = []
+    for mode in ("coop", "peer"):
+        p = K.KGMT(**cfg, seed=5, max_candidates=M); p.set_obstacles(obs)
+        p.seed_frontier(parents, w.C2_GOAL); p.set_children(M // P)
+        if mode == "coop":
+            st = p.iterate()
+        else:
+            p.peer_attach_local(0, [p])
+            st = p.peer_iterate()
+            p.peer_detach()
+        assert st["candidates"] == M and st["children"] == M // P and st["frontier"] == P
+        maps = {k: p.export(k) for k in (K.ARR_R1, K.ARR_R1VALID, K.ARR_R1INVALID, K.ARR_R2, K.ARR_R2VALID, K.ARR_R2INVALID, K.ARR_R2AVAIL)}
+        par = p.export(K.ARR_PARENT)[: st["tree_size"]].copy()
+        out.append((st, maps, par))
+        p.close()
+    (sa, ma, pa), (sb, mb, pb) = out
+    assert sa == sb
+    for k in ma:
+        np.testing.assert_array_equal(ma[k], mb[k])
+    np.testing.assert_array_equal(pa, pb)
+    # every candidate that ended inside the workspace is counted exactly once, valid or invalid
+    assert int(ma[K.ARR_R1].sum()) == int(ma[K.ARR_R1VALID].sum()) + int(ma[K.ARR_R1INVALID].sum()) <= M + P
+    assert int(ma[K.ARR_R1].sum()) >= int(0.8 * M)
+    assert sa["accepted"] == sa["tree_size"] - P and (np.diff(pa[P:]) >= 0).all() and pa[P:].max() < P
