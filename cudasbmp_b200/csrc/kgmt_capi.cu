@@ -61,6 +61,8 @@ struct kgmt_ctx {
     int cullC = 1, cellStartInts = 4, numItems = 0;
     float cullInvX = 0.f, cullInvY = 0.f;
     std::vector<float> hObs;
+    std::vector<int> hStart; std::vector<float> hItems, hObsPadded;   /* staging of the asynchronous uploads */
+    std::vector<unsigned char> hPath;  /* staging of kgmt_extract_path */
     /* staging */
     void* scratch = nullptr; size_t scratchBytes = 0;
     float4* dParents = nullptr; size_t parentsCap = 0;
@@ -278,7 +280,8 @@ static int build_cull_grid(kgmt_ctx* ctx) {
     if (C <= 0) C = (int)std::ceil(std::sqrt((double)std::max(K, 1)));
     C = std::max(1, std::min(C, 512));
     const float invX = (float)C / ctx->p.width, invY = (float)C / ctx->p.height;
-    std::vector<int> start((size_t)C * C + 1, 0);
+    std::vector<int>& start = ctx->hStart;
+    start.assign((size_t)C * C + 1, 0);
     const float* o = ctx->hObs.data();
     for (int k = 0; k < K; ++k) {
         const int x0 = cull_cell(o[4 * k], invX, C), x1 = cull_cell(o[4 * k + 2], invX, C);
@@ -289,7 +292,8 @@ static int build_cull_grid(kgmt_ctx* ctx) {
     for (size_t i = 0; i < (size_t)C * C; ++i) start[i + 1] += start[i];
     const int realItems = start[(size_t)C * C];
     const int numItems = realItems + 3;          /* + three boxes nothing overlaps: the cell walk reads four entries per trip */
-    std::vector<float> items((size_t)numItems * 4, 0.0f);
+    std::vector<float>& items = ctx->hItems;
+    items.assign((size_t)numItems * 4, 0.0f);
     for (int k = realItems; k < numItems; ++k) {
         items[(size_t)k * 4] = INFINITY; items[(size_t)k * 4 + 1] = INFINITY;
         items[(size_t)k * 4 + 2] = -INFINITY; items[(size_t)k * 4 + 3] = -INFINITY;
@@ -319,7 +323,6 @@ static int build_cull_grid(kgmt_ctx* ctx) {
     CU(cudaMemcpyAsync(ctx->dCellStart, start.data(), (size_t)startInts * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (numItems)
         CU(cudaMemcpyAsync(ctx->dCellItems, items.data(), (size_t)numItems * 16, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));     /* host vectors go out of scope */
     ctx->cullC = C; ctx->cullInvX = invX; ctx->cullInvY = invY; ctx->cellStartInts = startInts; ctx->numItems = numItems;
     return KGMT_OK;
 }
@@ -334,13 +337,13 @@ static int install_obstacles(kgmt_ctx* ctx) {
         ctx->obsCap = padded;
     }
     {
-        std::vector<float> h(padded * 4);
-        if (K) memcpy(h.data(), ctx->hObs.data(), (size_t)K * 16);
+        std::vector<float>& h = ctx->hObsPadded;      /* outlives the asynchronous copy (set_obstacles synchronises first) */
+        h.assign(padded * 4, 0.0f);
+        if (K > 0) memcpy(h.data(), ctx->hObs.data(), std::min(ctx->hObs.size(), (size_t)K * 4) * sizeof(float));
         for (size_t k = (size_t)K; k < padded; ++k) {
             h[4 * k] = INFINITY; h[4 * k + 1] = INFINITY; h[4 * k + 2] = -INFINITY; h[4 * k + 3] = -INFINITY;
         }
         CU(cudaMemcpyAsync(ctx->dObs, h.data(), padded * 16, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
     }
     int rc = build_cull_grid(ctx);
     if (rc) return rc;
@@ -1357,25 +1360,30 @@ int kgmt_import(kgmt_ctx* ctx, int id, const void* h_src, size_t bytes) {
 int kgmt_extract_path(kgmt_ctx* ctx, int node, float* h_rows7, int max_rows) {
     if (!ctx || max_rows < 0 || (max_rows > 0 && !h_rows7)) return KGMT_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
-    int rc = fetch_state(ctx);
-    if (rc) return rc;
+    /* the host copy of the scalars is current after every call of this library except between peer begin / end */
+    if (ctx->peer.inFlight) { int rc0 = fetch_state(ctx); if (rc0) return rc0; }
     const int T = ctx->hState->treeSize;
     if (node < 0) node = ctx->hState->goalIdx;
     if (node < 0 || node >= T) return fail(ctx, KGMT_ERR_INVALID, "no such node %d (tree size %d)", node, T);
-    /* back-trace on the device (one thread walks the parent links, L2-resident), one D2H of the rows it found */
+    /* back-trace on the device (the parent links are L2-resident), then ONE device-to-host copy of the length and the
+     * first rows (solution paths are a few dozen nodes); a second copy only for longer chains */
     const size_t rowsCap = (size_t)std::max(max_rows, 0);
-    rc = ensure_scratch(ctx, 16 + rowsCap * 28);
+    int rc = ensure_scratch(ctx, 16 + rowsCap * 28);
     if (rc) return rc;
     const KArgs A = make_args(ctx);
     trace_path_kernel<<<1, 32, 0, ctx->stream>>>(A, node, T, (int*)ctx->scratch, (float*)((char*)ctx->scratch + 16), max_rows);
     CU(cudaGetLastError());
     ctx->launches += 1;
-    int len = 0;
-    CU(cudaMemcpyAsync(&len, ctx->scratch, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t first = std::min<size_t>(rowsCap, 128);
+    ctx->hPath.resize(16 + first * 28);
+    CU(cudaMemcpyAsync(ctx->hPath.data(), ctx->scratch, 16 + first * 28, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    const int rows = std::min(len, max_rows);
-    if (rows > 0) {
-        CU(cudaMemcpyAsync(h_rows7, (char*)ctx->scratch + 16, (size_t)rows * 28, cudaMemcpyDeviceToHost, ctx->stream));
+    int len = 0;
+    memcpy(&len, ctx->hPath.data(), 4);
+    const size_t rows = std::min<size_t>((size_t)std::max(len, 0), rowsCap);
+    memcpy(h_rows7, ctx->hPath.data() + 16, std::min(rows, first) * 28);
+    if (rows > first) {
+        CU(cudaMemcpyAsync(h_rows7 + first * 7, (char*)ctx->scratch + 16 + first * 28, (rows - first) * 28, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return len;
