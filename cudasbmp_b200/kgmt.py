@@ -247,7 +247,7 @@ class KGMT:
         self.treeSize_, self.costToGoal_ = r.tree_size, r.cost_to_goal
         return r.as_dict()
 
-    def plan_batch(self, inits, goals, seeds, cluster_size=4, max_path=0):
+    def plan_batch(self, inits, goals, seeds, cluster_size=2, max_path=0):
         """Q independent queries on this planner's map in one launch (kgmt_plan_batch).
         Returns (results: list of dict, device_ms, paths: list of np [L,7] or None, workspaces)."""
         a = _f32(inits).reshape(-1, 7)
