@@ -100,6 +100,37 @@ def test_bit_exact_against_reference_cuda_kernels(oracle, mode, case):
     assert (np.bincount(r2[ok & (valid == 0)], minlength=c2) == maps["R2Invalid"]).all()
 
 
+def test_bit_exact_against_reference_kernels_large_and_extreme_headings(oracle):
+    """The same comparison at scale (262 144 edges on the config-2 map) and with parents whose heading is far outside
+    the fast range of the trigonometric range reduction (|theta| up to 1e7: libdevice's Payne-Hanek path, which
+    sincosf shares with the reference's separate sinf / cosf) and with large speeds (long steps, several cull cells
+    per step)."""
+    _ref_gpu_or_skip(oracle)
+    obstacles = w.c2_obstacles(1000)
+    N, n = 16, 8
+    P, children, key = 8192, 32, 90210
+    M = P * children
+    parents = w.random_parents(P, obstacles, seed=23)
+    rng = np.random.default_rng(5)
+    parents[: P // 2, 2] = (rng.uniform(-1.0, 1.0, P // 2) * 10.0 ** rng.integers(2, 8, P // 2)).astype(np.float32)
+    parents[P // 4: 3 * P // 4, 3] = rng.uniform(-40.0, 40.0, P // 2).astype(np.float32)
+    cfg = dict(w.C1, maxTreeSize=M)
+    c1, c2 = N * N, N * N * n * n
+    for mode in (K.COLLIDE_GRID, K.COLLIDE_BRUTE):
+        plan = _plan(cfg, obstacles, collision_mode=mode, record_candidates=True)
+        x1, valid, u3, r1, r2 = _propagate(plan, parents, children, key, M)
+        maps = {k: np.zeros(c1 if k.startswith("R1") else c2, dtype=np.int32)
+                for k in ("R1", "R2", "R1Valid", "R2Valid", "R1Invalid", "R2Invalid", "R1Avail", "R2Avail")}
+        unx, upar, gnew, _ = oracle.ref_gpu_expand(1, children, parents, np.arange(P, dtype=np.int32), maps,
+                                                   np.ones(c1, dtype=np.float32), N, n, plan.R1Size_, plan.R2Size_, 10, 1.0,
+                                                   obstacles, 20.0, 20.0, key)
+        assert (bits(unx) == bits(x1)).all(), "states/controls differ from the reference kernel"
+        inside = r1 >= 0
+        assert (gnew[inside] == valid[inside]).all(), "collision flags differ from the reference kernel"
+        assert (np.bincount(r1[inside & (valid == 1)], minlength=c1) == maps["R1Valid"]).all()
+        assert 0.05 < valid.mean() < 0.95
+
+
 def test_insertion_bit_exact_against_reference_updateG(oracle):
     """scan + findInd + updateG of the reference (KGMT.cu:222-245,540-593) vs our ordered insertion."""
     _ref_gpu_or_skip(oracle)
