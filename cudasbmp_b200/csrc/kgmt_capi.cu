@@ -35,7 +35,7 @@ struct kgmt_ctx {
     int* mapSlab = nullptr;            /* [R1,R1Valid,R1Invalid,R1Avail,R1Cov,R1Score | R2,R2Valid,R2Invalid,R2Stamp] */
     int* mapSlabCkpt = nullptr;
     size_t mapSlabInts = 0;            /* the region maps (checkpointed, exchanged) */
-    size_t slabInts = 0;               /* + scan / pipeline bookkeeping behind them */
+    size_t slabInts = 0;               /* + scan bookkeeping behind them */
     int *R1 = nullptr, *R1Valid = nullptr, *R1Invalid = nullptr, *R1Avail = nullptr, *R1Cov = nullptr;
     float* R1Score[2] = {nullptr, nullptr};
     int *R2 = nullptr, *R2Valid = nullptr, *R2Invalid = nullptr;
@@ -45,8 +45,6 @@ struct kgmt_ctx {
     unsigned char* candFlags = nullptr;
     bool recordAllocated = false;
     unsigned* chunkMask = nullptr; int* blockSum = nullptr; unsigned* ticket = nullptr;
-    int* blockDone = nullptr; int* blockPrefix = nullptr; int* blockInserted = nullptr; PipeIter* pipeCtl = nullptr;   /* pipelined loop */
-    int pipe = 0;                      /* 1: kgmt_plan / kgmt_expand_iterations run the barrier-free loop (run_plan_pipe) */
     int raceId = 0;                    /* > 0 while kgmt_peer_race runs */
     size_t chunksCap = 0, blocksCap = 0;
     float4 *stageState = nullptr, *stageCtrl = nullptr;
@@ -70,7 +68,7 @@ struct kgmt_ctx {
     int col = COL_GRID_SMEM; size_t smemBytes = 0; int useHist = 0;
     int gridLoop = 0, gridMax = 0;
     bool configured = false;
-    int cfgCol = -1, cfgPipe = -1; size_t cfgSmem = 0;      /* what the launch configuration was resolved for */
+    int cfgCol = -1; size_t cfgSmem = 0;      /* what the launch configuration was resolved for */
     bool begun = false;
     float goal[7] = {0};
     long long launches = 0;
@@ -119,14 +117,7 @@ static int fail(kgmt_ctx* c, int code, const char* fmt, ...) {
             return fail(ctx, KGMT_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
     } while (0)
 
-#ifdef KGMT_PIPE_PROF
-#define KGMT_ITERLOG_BYTES (256 * 64 + 8192 * 32 * 8)    /* + per-warp trace rows of 32 words (debug build) */
-#else
 #define KGMT_ITERLOG_BYTES (256 * 64)
-#endif
-#ifndef KGMT_DEFAULT_LOOP
-#define KGMT_DEFAULT_LOOP 2          /* 1 = pipelined, 2 = grid barrier */
-#endif
 static const size_t MAX_DYN_SMEM = 227u * 1024u - 8u * 1024u;   /* leave room for static shared + reserve */
 
 /* -------------------------------------------------------------------------------- kernels table */
@@ -141,17 +132,6 @@ static expand_fn expand_entry(int col, bool rec) {
         case COL_BRUTE_SMEM: return pick_expand<COL_BRUTE_SMEM>(rec);
         case COL_BRUTE_STREAM: return pick_expand<COL_BRUTE_STREAM>(rec);
         default: return pick_expand<COL_BRUTE_GLOBAL>(rec);
-    }
-}
-template <int COL> static expand_fn pick_pipe(bool rec) {
-    return rec ? (expand_fn)expand_pipe_kernel<COL, true> : (expand_fn)expand_pipe_kernel<COL, false>;
-}
-static expand_fn pipe_entry(int col, bool rec) {
-    switch (col) {
-        case COL_GRID_SMEM: return pick_pipe<COL_GRID_SMEM>(rec);
-        case COL_GRID_GLOBAL: return pick_pipe<COL_GRID_GLOBAL>(rec);
-        case COL_BRUTE_SMEM: return pick_pipe<COL_BRUTE_SMEM>(rec);
-        default: return pick_pipe<COL_BRUTE_GLOBAL>(rec);
     }
 }
 typedef void (*prop_fn)(const KArgs, const float4*, long long, int, uint32_t, uint32_t);
@@ -186,7 +166,6 @@ static KArgs make_args(const kgmt_ctx* c) {
     A.chunkMask = c->chunkMask; A.blockSum = c->blockSum; A.ticket = c->ticket;
     A.stageState = c->stageState; A.stageCtrl = c->stageCtrl;
     A.chunksCap = (int)c->chunksCap; A.blocksCap = (int)c->blocksCap; A.maxCand = c->maxCand; A.totalWarps = c->gridLoop * WARPS;
-    A.blockDone = c->blockDone; A.blockPrefix = c->blockPrefix; A.blockInserted = c->blockInserted; A.pipe = c->pipeCtl; A.pipeMode = c->pipe;
     A.raceId = c->raceId; A.raceWorld = c->peer.world; A.raceRank = c->peer.rank; A.raceFlags = c->peer.dRaceFlags;
     A.st = c->dState;
     A.obstacles = c->dObs; A.K = c->K;
@@ -199,6 +178,9 @@ static KArgs make_args(const kgmt_ctx* c) {
     A.N = c->p.N; A.n = c->p.n; A.c1 = c->c1; A.numDisc = c->p.num_disc; A.maxTree = c->p.max_tree_size;
     A.numIterations = c->p.num_iterations; A.useHist = c->useHist;
     A.seed = c->p.seed;
+    A.car.aScale = (float)(c->p.accel_max - c->p.accel_min); A.car.aLo = (float)c->p.accel_min;
+    A.car.sScale = c->p.steer_max - c->p.steer_min;          A.car.sLo = c->p.steer_min;
+    A.car.dScale = (float)(c->p.duration_max - c->p.duration_min); A.car.dLo = (float)c->p.duration_min;
     return A;
 }
 
@@ -221,20 +203,13 @@ static int configure(kgmt_ctx* ctx) {
     if (col == COL_GRID_GLOBAL || col == COL_BRUTE_GLOBAL) colBytes = 0;
     ctx->col = col;
     ctx->smemBytes = histBytes + colBytes;
-    /* loop flavour: reserved[2] = 1 barrier-free pipelined loop, 2 = grid-barrier loop, 0 = default (environment
-     * variable KGMT_PIPE, else pipelined); the tile-streamed back end only exists in the grid-barrier loop */
-    {
-        int want = ctx->p.reserved[2];
-        if (want == 0) { const char* e = getenv("KGMT_PIPE"); want = e ? (atoi(e) ? 1 : 2) : KGMT_DEFAULT_LOOP; }
-        ctx->pipe = (want == 1 && col != COL_BRUTE_STREAM) ? 1 : 0;
-    }
     /* a new obstacle set of the same size class resolves to the same kernels and shared-memory size: keep the launch
      * configuration (the attribute / occupancy queries below are ~100 us of driver calls per kgmt_set_obstacles) */
-    if (ctx->configured && ctx->cfgCol == col && ctx->cfgSmem == ctx->smemBytes && ctx->cfgPipe == ctx->pipe) return KGMT_OK;
-    ctx->cfgCol = col; ctx->cfgSmem = ctx->smemBytes; ctx->cfgPipe = ctx->pipe;
+    if (ctx->configured && ctx->cfgCol == col && ctx->cfgSmem == ctx->smemBytes) return KGMT_OK;
+    ctx->cfgCol = col; ctx->cfgSmem = ctx->smemBytes;
     int occ = 1 << 30;
     for (int rec = 0; rec < 2; ++rec) {
-        expand_fn f = ctx->pipe ? pipe_entry(col, rec != 0) : expand_entry(col, rec != 0);
+        expand_fn f = expand_entry(col, rec != 0);
         CU(cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemBytes));
         int o = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void*)f, TILE, ctx->smemBytes));
@@ -401,7 +376,7 @@ static int clear_state(kgmt_ctx* ctx, bool sync, bool light = false) {
     if (light) return KGMT_OK;
     fill_float_kernel<<<(2 * ctx->c1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->R1Score[0], 1.0f, (size_t)2 * ctx->c1);
     DevState z{};
-    z.goalIdx = -1; z.goalSlot = -1; z.goalBest = ~0ull; z.stop = STOP_ITER_LIMIT; z.itr = 1;
+    z.goalIdx = -1; z.goalSlot = -1; z.goalBest[0] = z.goalBest[1] = ~0ull; z.stop = STOP_ITER_LIMIT; z.itr = 1;
     z.forceChildren = ctx->hState->forceChildren;
     ctx->resetState = z;
     CU(cudaMemcpyAsync(ctx->dState, &ctx->resetState, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
@@ -412,16 +387,13 @@ static int clear_state(kgmt_ctx* ctx, bool sync, bool light = false) {
     return KGMT_OK;
 }
 
-/* scan/ticket/pipeline bookkeeping back to "between two iterations, nothing in flight" (after a restore or a sharded
+/* scan/ticket bookkeeping back to "between two iterations, nothing in flight" (after a restore or a sharded
  * round, which do not run the planner loops' own recycling) */
 static int reset_loop_bookkeeping(kgmt_ctx* ctx) {
-    const unsigned t0 = ctx->pipe ? 0u : (unsigned)(ctx->gridLoop * WARPS);
+    const unsigned t0 = (unsigned)(ctx->gridLoop * WARPS);
     const unsigned tk[4] = {t0, t0, t0, 0u};
     CU(cudaMemcpyAsync(ctx->ticket, tk, 16, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(ctx->blockSum, 0, 3 * ctx->blocksCap * 4, ctx->stream));
-    CU(cudaMemsetAsync(ctx->blockDone, 0, 3 * ctx->blocksCap * 4, ctx->stream));
-    CU(cudaMemsetAsync(ctx->blockInserted, 0, 3 * ctx->blocksCap * 4, ctx->stream));
-    CU(cudaMemsetAsync(ctx->pipeCtl, 0, 3 * sizeof(PipeIter), ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return KGMT_OK;
 }
@@ -471,6 +443,76 @@ void kgmt_default_params(kgmt_params* p) {
     p->num_disc = 10; p->agent_length = 1.0f; p->goal_threshold = 0.5f;
     p->seed = 1u; p->device = -1; p->max_candidates = 0; p->collision_mode = KGMT_COLLIDE_GRID;
     p->record_candidates = 0; p->cull_cells = 0;
+    /* statePropagator.cu:17-19 */
+    p->accel_min = -5.0; p->accel_max = 5.0;
+    p->steer_min = -3.14159265358979323846; p->steer_max = 3.14159265358979323846;
+    p->duration_min = (double)0.05f; p->duration_max = (double)0.05f + 1.0;
+}
+
+/* ---- car model file (the reference ships systems/car.yaml EMPTY and hard-codes the model) ---- */
+int kgmt_params_from_yaml(const char* path, kgmt_params* p, int* bad_line) {
+    if (bad_line) *bad_line = 0;
+    if (!path || !p) return KGMT_ERR_INVALID;
+    FILE* f = fopen(path, "r");
+    if (!f) return KGMT_ERR_INVALID;
+    char line[512];
+    int ln = 0, rc = KGMT_OK;
+    while (fgets(line, sizeof(line), f)) {
+        ++ln;
+        char* hash = strchr(line, '#');
+        if (hash) *hash = 0;
+        char* s = line;
+        while (*s == ' ' || *s == '\t') ++s;
+        char* e = s + strlen(s);
+        while (e > s && (e[-1] == '\n' || e[-1] == '\r' || e[-1] == ' ' || e[-1] == '\t')) *--e = 0;
+        if (!*s || !strcmp(s, "---") || !strcmp(s, "...")) continue;
+        char* colon = strchr(s, ':');
+        if (!colon) { rc = KGMT_ERR_INVALID; break; }
+        *colon = 0;
+        char* key = s;
+        char* ke = colon;
+        while (ke > key && (ke[-1] == ' ' || ke[-1] == '\t')) *--ke = 0;
+        char* val = colon + 1;
+        while (*val == ' ' || *val == '\t') ++val;
+        if (!*val) continue;                                   /* "controls:" — a block header, flattened */
+        char* endp = nullptr;
+        double v = strtod(val, &endp);
+        bool num = endp != val;
+        if (num) { while (*endp == ' ') ++endp; num = (*endp == 0); }
+        if (!num) {
+            /* the one non-numeric spelling worth having: bounds in units of pi ("pi", "-pi", "0.5pi", "2*pi") */
+            const char* q = val;
+            double k = 1.0;
+            char* e2 = nullptr;
+            const double kk = strtod(q, &e2);
+            if (e2 != q) { k = kk; q = e2; }
+            else if (*q == '-') { k = -1.0; ++q; }
+            else if (*q == '+') { ++q; }
+            while (*q == ' ' || *q == '*') ++q;
+            if (!strcmp(q, "pi") || !strcmp(q, "PI") || !strcmp(q, "M_PI")) { num = true; v = k * 3.14159265358979323846; }
+        }
+        if (!num) { rc = KGMT_ERR_INVALID; break; }
+        if (!strcmp(key, "wheelbase") || !strcmp(key, "agent_length") || !strcmp(key, "length")) p->agent_length = (float)v;
+        else if (!strcmp(key, "num_disc") || !strcmp(key, "numDisc")) p->num_disc = (int)v;
+        else if (!strcmp(key, "accel_min")) p->accel_min = v;
+        else if (!strcmp(key, "accel_max")) p->accel_max = v;
+        else if (!strcmp(key, "steer_min") || !strcmp(key, "steering_min")) p->steer_min = v;
+        else if (!strcmp(key, "steer_max") || !strcmp(key, "steering_max")) p->steer_max = v;
+        else if (!strcmp(key, "duration_min")) p->duration_min = v;
+        else if (!strcmp(key, "duration_max")) p->duration_max = v;
+        else if (!strcmp(key, "width")) p->width = (float)v;
+        else if (!strcmp(key, "height")) p->height = (float)v;
+        else if (!strcmp(key, "N")) p->N = (int)v;
+        else if (!strcmp(key, "n")) p->n = (int)v;
+        else if (!strcmp(key, "num_iterations")) p->num_iterations = (int)v;
+        else if (!strcmp(key, "max_tree_size")) p->max_tree_size = (int)v;
+        else if (!strcmp(key, "goal_threshold")) p->goal_threshold = (float)v;
+        else if (!strcmp(key, "seed")) p->seed = (uint32_t)v;
+        else { rc = KGMT_ERR_INVALID; break; }
+    }
+    fclose(f);
+    if (rc && bad_line) *bad_line = ln;
+    return rc;
 }
 
 const char* kgmt_last_error(const kgmt_ctx* ctx) { return ctx ? ctx->err : "null context"; }
@@ -484,7 +526,7 @@ void kgmt_destroy(kgmt_ctx* ctx) {
     cudaFree(ctx->mapSlab); cudaFree(ctx->mapSlabCkpt);
     cudaFree(ctx->candState); cudaFree(ctx->candCtrl); cudaFree(ctx->candParent);
     cudaFree(ctx->candR1); cudaFree(ctx->candR2); cudaFree(ctx->candFlags);
-    cudaFree(ctx->chunkMask); cudaFree(ctx->ticket); cudaFree(ctx->blockPrefix);
+    cudaFree(ctx->chunkMask); cudaFree(ctx->ticket);
     cudaFree(ctx->stageState); cudaFree(ctx->stageCtrl);
     cudaFree(ctx->dState); cudaFree(ctx->iterLog);
     if (ctx->hState) cudaFreeHost(ctx->hState);
@@ -512,6 +554,19 @@ int kgmt_create(const kgmt_params* p, kgmt_ctx** out) {
     if (!ctx) return KGMT_ERR_NOMEM;
     *out = ctx;                                   /* returned even on failure so the caller can read the error */
     ctx->p = *p;
+    {   /* car model: all-zero ranges (a caller that filled the struct by hand) mean the reference's literals */
+        kgmt_params& q = ctx->p;
+        if (q.accel_min == 0.0 && q.accel_max == 0.0 && q.steer_min == 0.0 && q.steer_max == 0.0 &&
+            q.duration_min == 0.0 && q.duration_max == 0.0) {
+            kgmt_params d; kgmt_default_params(&d);
+            q.accel_min = d.accel_min; q.accel_max = d.accel_max; q.steer_min = d.steer_min; q.steer_max = d.steer_max;
+            q.duration_min = d.duration_min; q.duration_max = d.duration_max;
+        }
+        const double r[6] = {q.accel_min, q.accel_max, q.steer_min, q.steer_max, q.duration_min, q.duration_max};
+        for (double v : r) if (!std::isfinite(v)) return fail(ctx, KGMT_ERR_INVALID, "control range is not finite");
+        if (q.accel_max < q.accel_min || q.steer_max < q.steer_min || q.duration_max < q.duration_min || q.duration_min < 0.0)
+            return fail(ctx, KGMT_ERR_INVALID, "control range: max < min, or negative duration");
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -545,8 +600,8 @@ int kgmt_create(const kgmt_params* p, kgmt_ctx** out) {
     ctx->mapSlabInts = 7 * c1 + 4 * c2;
     ctx->chunksCap = ((size_t)ctx->maxCand + CHUNK - 1) / CHUNK + 1;
     ctx->blocksCap = (ctx->chunksCap + BLK_CHUNKS - 1) / BLK_CHUNKS + 1;
-    /* one slab: region maps, then the per-iteration scan / pipeline bookkeeping — a re-plan clears all of it with ONE memset */
-    const size_t bookInts = 9 * ctx->blocksCap + 3 * (sizeof(PipeIter) / 4);
+    /* one slab: region maps, then the per-iteration scan block sums — a re-plan clears all of it with ONE memset */
+    const size_t bookInts = 3 * ctx->blocksCap;
     ctx->slabInts = ((ctx->mapSlabInts + 3) & ~(size_t)3) + bookInts;
     CU(cudaMalloc(&ctx->mapSlab, ctx->slabInts * 4));
     int* m = ctx->mapSlab;
@@ -556,11 +611,9 @@ int kgmt_create(const kgmt_params* p, kgmt_ctx** out) {
     ctx->R2 = m; m += c2; ctx->R2Valid = m; m += c2; ctx->R2Invalid = m; m += c2;
     ctx->R2Stamp = reinterpret_cast<unsigned*>(m);
     m = ctx->mapSlab + ((ctx->mapSlabInts + 3) & ~(size_t)3);
-    ctx->blockSum = m; m += 3 * ctx->blocksCap; ctx->blockDone = m; m += 3 * ctx->blocksCap;
-    ctx->blockInserted = m; m += 3 * ctx->blocksCap; ctx->pipeCtl = reinterpret_cast<PipeIter*>(m);
+    ctx->blockSum = m;
     CU(cudaMalloc(&ctx->chunkMask, 2 * ctx->chunksCap * 4));
     CU(cudaMalloc(&ctx->ticket, 4 * 4));
-    CU(cudaMalloc(&ctx->blockPrefix, 3 * ctx->blocksCap * 4));
     CU(cudaMalloc(&ctx->stageState, 2 * (size_t)ctx->maxCand * 16));
     CU(cudaMalloc(&ctx->stageCtrl, 2 * (size_t)ctx->maxCand * 16));
     CU(cudaMemsetAsync(ctx->chunkMask, 0, 2 * ctx->chunksCap * 4, ctx->stream));
@@ -625,8 +678,7 @@ int kgmt_begin(kgmt_ctx* ctx, const float* initial7, const float* goal7) {
 
 static int launch_expand(kgmt_ctx* ctx, int maxIters) {
     KArgs A = make_args(ctx);
-    expand_fn f = ctx->pipe ? pipe_entry(ctx->col, ctx->p.record_candidates != 0)
-                            : expand_entry(ctx->col, ctx->p.record_candidates != 0);
+    expand_fn f = expand_entry(ctx->col, ctx->p.record_candidates != 0);
     void* args[] = {(void*)&A, (void*)&maxIters};
     CU(cudaLaunchCooperativeKernel((const void*)f, dim3(ctx->gridLoop), dim3(TILE), args, ctx->smemBytes, ctx->stream));
     ctx->launches += 1;
@@ -752,7 +804,6 @@ int kgmt_plan_batch(kgmt_ctx* ctx, const float* h_inits7, const float* h_goals7,
     B.base.stageState = b.stageState; B.base.stageCtrl = b.stageCtrl;
     B.base.candState = nullptr; B.base.candCtrl = nullptr; B.base.candParent = nullptr; B.base.candR1 = nullptr;
     B.base.candR2 = nullptr; B.base.candFlags = nullptr; B.base.iterLog = nullptr;
-    B.base.pipeMode = 0;                                   /* the cluster loop is the barrier loop: tickets start at totalWarps */
     B.Q = Q; B.numWorkspaces = numWs;
     B.initState = b.initState; B.initCtrl = b.initCtrl; B.goalXY = b.goalXY; B.seeds = b.seeds; B.states = b.states;
     B.paths = wantPath ? b.paths : nullptr; B.pathLen = b.pathLen; B.maxPath = wantPath;
@@ -884,7 +935,6 @@ int kgmt_shard_commit(kgmt_ctx* ctx, const void* d_recv, int cap_rows, const int
         ctx->launches += total > 0 ? 3 : 2;
     }
     ctx->shardAccepted = -1;
-    if (ctx->pipe) { int rc2 = reset_loop_bookkeeping(ctx); if (rc2) return rc2; }
     int rc = fetch_state(ctx);
     if (rc) return rc;
     if (out) {
@@ -945,6 +995,10 @@ int kgmt_peer_export(kgmt_ctx* ctx, void* out_handles, size_t bytes) {
 }
 
 static int peer_publish_tables(kgmt_ctx* ctx) {
+    /* a re-attached context restarts its exchange sequence at 0: clear what earlier exchanges left in THIS rank's
+     * mailboxes and race word (stale seq words would satisfy the first waits).  Every rank must have attached before
+     * any rank starts an exchange — the host program barriers after kgmt_peer_attach. */
+    CU(cudaMemset(ctx->peer.block + ctx->peer.mailOff, 0, ctx->peer.blockBytes - ctx->peer.mailOff));
     int* flags[PEER_MAX] = {};
     for (int p = 0; p < ctx->peer.world; ++p) flags[p] = (int*)((unsigned char*)ctx->peer.args.delta[p] + ctx->peer.raceOff);
     CU(cudaMemcpy(ctx->peer.dRaceFlags, flags, sizeof(flags), cudaMemcpyHostToDevice));
@@ -1033,7 +1087,6 @@ int kgmt_peer_attach_local(kgmt_ctx* ctx, int rank, int world, kgmt_ctx* const* 
 int kgmt_peer_race(kgmt_ctx* ctx, const float* initial7, const float* goal7, int race_id, kgmt_result* out) {
     if (!ctx || race_id <= 0) return fail(ctx, KGMT_ERR_INVALID, "race_id must be positive");
     if (ctx->peer.rank < 0) return fail(ctx, KGMT_ERR_STATE, "kgmt_peer_race before kgmt_peer_attach");
-    if (ctx->pipe) return fail(ctx, KGMT_ERR_STATE, "kgmt_peer_race needs the grid-barrier loop (params.reserved[2] = 2)");
     ctx->raceId = race_id;
     const int rc = kgmt_plan(ctx, initial7, goal7, out);
     ctx->raceId = 0;
@@ -1096,7 +1149,6 @@ int kgmt_peer_expand_end(kgmt_ctx* ctx, kgmt_iter_stats* out) {
     int rc = fetch_state(ctx);
     if (rc) return rc;
     if (ran && pr.hPlan->err) return fail(ctx, KGMT_ERR_COMM, "a peer did not arrive within 5 s (rank %d of %d, exchange %d)", pr.rank, pr.world, pr.seq);
-    if (ran && ctx->pipe) { rc = reset_loop_bookkeeping(ctx); if (rc) return rc; }
     if (out) {
         const DevState& s = *ctx->hState;
         out->iteration = s.lastItr; out->mode = s.lastMode; out->children = s.lastChildren; out->frontier = s.lastFrontier;
@@ -1173,6 +1225,74 @@ int kgmt_seed_frontier(kgmt_ctx* ctx, const float* h_nodes7, int count, const fl
     return fetch_state(ctx);
 }
 
+/* Stage 5a alone on caller-supplied candidates (see kgmt_c.h): upload the records, then the planner's own chunk_finish. */
+int kgmt_stage_update_maps(kgmt_ctx* ctx, const float* h_cand7, const unsigned char* h_valid, const float* h_u3,
+                           const int* h_parent, int M) {
+    if (!ctx || !h_cand7 || !h_valid || !h_u3 || !h_parent || M < 1) return fail(ctx, KGMT_ERR_INVALID, "bad candidate arrays");
+    if (!ctx->begun) return fail(ctx, KGMT_ERR_STATE, "kgmt_stage_update_maps before kgmt_begin / kgmt_seed_frontier");
+    if (M > ctx->maxCand) return fail(ctx, KGMT_ERR_INVALID, "M = %d exceeds max_candidates %d", M, ctx->maxCand);
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_record(ctx);
+    if (rc) return rc;
+    rc = fetch_state(ctx);
+    if (rc) return rc;
+    DevState& st = *ctx->hState;
+    if (st.stop != STOP_RUNNING) return fail(ctx, KGMT_ERR_STATE, "the planner has stopped (%d)", st.stop);
+    if ((long long)M > (long long)ctx->p.max_tree_size - st.treeSize)
+        return fail(ctx, KGMT_ERR_INVALID, "M = %d candidates could not all be inserted (tree has %d free rows)", M, ctx->p.max_tree_size - st.treeSize);
+    /* records in the device layout: float4 state | float4 (a, steering, duration, u3) | parent | flags */
+    std::vector<float> hs((size_t)M * 4), hc((size_t)M * 4);
+    std::vector<unsigned char> hf((size_t)M);
+    for (int i = 0; i < M; ++i) {
+        memcpy(&hs[(size_t)i * 4], &h_cand7[(size_t)i * 7], 16);
+        hc[(size_t)i * 4] = h_cand7[(size_t)i * 7 + 4]; hc[(size_t)i * 4 + 1] = h_cand7[(size_t)i * 7 + 5];
+        hc[(size_t)i * 4 + 2] = h_cand7[(size_t)i * 7 + 6]; hc[(size_t)i * 4 + 3] = h_u3[i];
+        hf[i] = h_valid[i] ? FLAG_VALID : 0;
+    }
+    cudaStream_t s = ctx->stream;
+    CU(cudaMemcpyAsync(ctx->candState, hs.data(), (size_t)M * 16, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->candCtrl, hc.data(), (size_t)M * 16, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->candParent, h_parent, (size_t)M * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ctx->candFlags, hf.data(), (size_t)M, cudaMemcpyHostToDevice, s));
+    /* the pending iteration now has exactly these candidates (mode 5 = staged by the caller) */
+    st.mode = 5; st.children = 1; st.M = M; st.numChunks = (M + CHUNK - 1) / CHUNK;
+    CU(cudaMemcpyAsync(ctx->dState, ctx->hState, COPIED_WORDS * 4, cudaMemcpyHostToDevice, s));
+    rc = reset_loop_bookkeeping(ctx);               /* clean block sums, whatever ran before */
+    if (rc) return rc;
+    KArgs A = make_args(ctx);
+    A.useHist = 0;                                  /* R1 counters straight to global memory */
+    const int grid = std::max(1, std::min((st.numChunks + WARPS - 1) / WARPS, ctx->numSMs * 8));
+    stage_update_kernel<<<grid, TILE, 0, s>>>(A);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    ctx->dirtyCand = ctx->maxCand;
+    CU(cudaStreamSynchronize(s));                   /* the host staging vectors go out of scope */
+    return KGMT_OK;
+}
+
+/* Stage 5b alone: ordered insertion of what kgmt_stage_update_maps accepted + the end of the while-loop body. */
+int kgmt_stage_insert(kgmt_ctx* ctx, kgmt_iter_stats* out) {
+    if (!ctx) return KGMT_ERR_INVALID;
+    if (!ctx->begun || !ctx->recordAllocated || ctx->hState->mode != 5)
+        return fail(ctx, KGMT_ERR_STATE, "kgmt_stage_insert needs a preceding kgmt_stage_update_maps");
+    CU(cudaSetDevice(ctx->device));
+    const KArgs A = make_args(ctx);
+    stage_insert_kernel<<<1, TILE, 0, ctx->stream>>>(A);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    int rc = reset_loop_bookkeeping(ctx);
+    if (rc) return rc;
+    rc = fetch_state(ctx);
+    if (rc) return rc;
+    if (out) {
+        const DevState& s = *ctx->hState;
+        out->iteration = s.lastItr; out->mode = s.lastMode; out->children = s.lastChildren; out->frontier = s.lastFrontier;
+        out->candidates = s.lastM; out->accepted = s.lastAccepted; out->tree_size = s.treeSize; out->stop = s.stop;
+        out->cost_to_goal = s.costToGoal; out->goal_index = s.goalIdx;
+    }
+    return KGMT_OK;
+}
+
 /* kgmt_set_children: > 0 forces that many children per frontier node in every later iteration
  * (throughput sweeps, BASELINE config 5); 0 restores the reference policy (KGMT.cu:151-158). */
 int kgmt_set_children(kgmt_ctx* ctx, int children) {
@@ -1188,7 +1308,7 @@ int kgmt_set_children(kgmt_ctx* ctx, int children) {
         if (children > 0 && (long long)st.frontierCount * children > std::min<long long>(remaining, ctx->maxCand))
             return fail(ctx, KGMT_ERR_INVALID, "frontier*children exceeds the remaining tree/candidate capacity");
         int mode, ch, M;
-        expansion_shape(st.frontierCount, st.treeSize, ctx->p.max_tree_size, children, mode, ch, M);
+        expansion_shape(st.frontierCount, st.treeSize, ctx->p.max_tree_size, ctx->maxCand, children, mode, ch, M);
         st.mode = mode; st.children = ch; st.M = M; st.numChunks = (M + CHUNK - 1) / CHUNK;
     }
     CU(cudaMemcpyAsync(ctx->dState, ctx->hState, sizeof(DevState), cudaMemcpyHostToDevice, ctx->stream));
@@ -1444,6 +1564,16 @@ float kgmt_r2_size(const kgmt_ctx* ctx) { return ctx ? ctx->R2Size : 0.f; }
 void* kgmt_stream(const kgmt_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 long long kgmt_launch_count(const kgmt_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int kgmt_work_counters(kgmt_ctx* ctx, unsigned long long* out4) {
+    if (!ctx || !out4) return KGMT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    int rc = fetch_state(ctx);
+    if (rc) return rc;
+    out4[0] = ctx->hState->stepsDone; out4[1] = ctx->hState->pairsTested;
+    out4[2] = (unsigned long long)ctx->hState->expansions; out4[3] = 0;
+    return KGMT_OK;
+}
+
 /* per-iteration device timestamps of the last plan (diagnostics): out[i] = {ns since the first logged iteration
  * ended... raw globaltimer ns, candidates, accepted}; returns the number of rows written (<= max_rows) */
 int kgmt_iteration_log(kgmt_ctx* ctx, int enable, unsigned long long* out8, int max_rows) {
@@ -1456,11 +1586,7 @@ int kgmt_iteration_log(kgmt_ctx* ctx, int enable, unsigned long long* out8, int 
     if (!out8 || max_rows <= 0 || !ctx->iterLog) return 0;
     int rc = fetch_state(ctx);
     if (rc) return rc;
-#ifdef KGMT_PIPE_PROF
-    const int n = std::min(256 + 8192 * 4, max_rows);   /* debug build: row 255 = per-phase warp-cycle totals, rows 256.. = warp traces */
-#else
     const int n = std::min(std::min(ctx->hState->iterationsDone, 255), max_rows);
-#endif
     CU(cudaMemcpy(out8, ctx->iterLog, (size_t)n * 64, cudaMemcpyDeviceToHost));
     return n;
 }

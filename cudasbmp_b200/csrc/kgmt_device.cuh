@@ -45,14 +45,22 @@ __device__ __forceinline__ float uniform01(uint32_t x) {
 
 struct Controls { float a, steering, duration, u3; };
 
+/* control ranges of the car model (kgmt_params: accel / steer / duration min..max), pre-reduced to scale and offset.
+ * The defaults {10, -5, 2*pi, -pi, 1, 0.05f} give the reference's literals of statePropagator.cu:17-19 bit for bit:
+ *   u0 * 10.0f - 5.0f            -> one FFMA;
+ *   u1 * 2.0f * M_PI - M_PI      -> DFMA((double)(u1 + u1), pi, -pi) == DFMA((double)u1, 2*pi, -pi): u1 + u1 and 2*pi
+ *                                   are exact doublings, so both products are the same real number, rounded once;
+ *   u2 * 1.0f + 0.05f            -> FFMA(u2, 1, 0.05f) == FADD(u2, 0.05f). */
+struct CarRanges { float aScale, aLo; double sScale, sLo; float dScale, dLo; };
+
 /* statePropagator.cu:17-19 (+ the accept uniform of KGMT.cu:395) */
-__device__ __forceinline__ Controls sample_controls(uint32_t slot, uint32_t key0) {
+__device__ __forceinline__ Controls sample_controls(uint32_t slot, uint32_t key0, const CarRanges& r) {
     const uint4 w = philox4x32_10(slot, key0);
     const float u0 = uniform01(w.x), u1 = uniform01(w.y), u2 = uniform01(w.z);
     Controls c;
-    c.a = __fmaf_rn(u0, 10.0f, -5.0f);
-    c.steering = __double2float_rn(__fma_rn((double)__fadd_rn(u1, u1), 3.14159265358979323846, -3.14159265358979323846));
-    c.duration = __fadd_rn(u2, 0.05f);
+    c.a = __fmaf_rn(u0, r.aScale, r.aLo);
+    c.steering = __double2float_rn(__fma_rn((double)u1, r.sScale, r.sLo));
+    c.duration = __fmaf_rn(u2, r.dScale, r.dLo);
     c.u3 = uniform01(w.w);
     return c;
 }
@@ -97,18 +105,19 @@ __device__ __forceinline__ bool aabb_overlap(float bnx, float bny, float bxx, fl
 /* every obstacle, shared-memory resident (float4 per obstacle, one broadcast LDS.128 each) */
 struct CollideSmemAll {
     const float4* obs; int K;
-    struct Cursor {};
-    __device__ __forceinline__ Cursor start(float, float) const { return Cursor{}; }
-    __device__ __forceinline__ bool hit(Cursor&, float, float, float bnx, float bny, float bxx, float bxy) const {
+    struct Cursor { unsigned pairs; };      /* pairs: overlap tests executed (read only by the recording kernels; dead code otherwise) */
+    __device__ __forceinline__ Cursor start(float, float) const { return Cursor{0u}; }
+    __device__ __forceinline__ bool hit(Cursor& cur, float, float, float bnx, float bny, float bxx, float bxy) const {
         bool h = false;
         int k = 0;
         for (; k + 4 <= K; k += 4) {
             const float4 o0 = obs[k], o1 = obs[k + 1], o2 = obs[k + 2], o3 = obs[k + 3];
             h = aabb_overlap(bnx, bny, bxx, bxy, o0) | aabb_overlap(bnx, bny, bxx, bxy, o1) |
                 aabb_overlap(bnx, bny, bxx, bxy, o2) | aabb_overlap(bnx, bny, bxx, bxy, o3);
+            cur.pairs += 4u;
             if (h) return true;
         }
-        for (; k < K; ++k) h |= aabb_overlap(bnx, bny, bxx, bxy, obs[k]);
+        for (; k < K; ++k) { h |= aabb_overlap(bnx, bny, bxx, bxy, obs[k]); cur.pairs += 1u; }
         return h;
     }
 };
@@ -123,11 +132,11 @@ struct CollideGrid {
     const int* cellStart;      /* [C*C+1] */
     const float4* items;       /* obstacle AABBs, grouped by cell */
     int C; float invX, invY;
-    struct Cursor { int cx, cy; };
+    struct Cursor { int cx, cy; unsigned pairs; };
     __device__ __forceinline__ int cell(float v, float inv) const {
         return min(max(__float2int_rd(__fmul_rn(v, inv)), 0), C - 1);
     }
-    __device__ __forceinline__ Cursor start(float x, float y) const { return Cursor{cell(x, invX), cell(y, invY)}; }
+    __device__ __forceinline__ Cursor start(float x, float y) const { return Cursor{cell(x, invX), cell(y, invY), 0u}; }
     __device__ __forceinline__ bool hit(Cursor& cur, float x, float y, float bnx, float bny, float bxx, float bxy) const {
         const int cxn = cell(x, invX), cyn = cell(y, invY);
         const int cx0 = min(cur.cx, cxn), cx1 = max(cur.cx, cxn);
@@ -145,6 +154,7 @@ struct CollideGrid {
                 const float4 o0 = items[k], o1 = items[k + 1], o2 = items[k + 2], o3 = items[k + 3];
                 h = aabb_overlap(bnx, bny, bxx, bxy, o0) | aabb_overlap(bnx, bny, bxx, bxy, o1) |
                     aabb_overlap(bnx, bny, bxx, bxy, o2) | aabb_overlap(bnx, bny, bxx, bxy, o3);
+                cur.pairs += 4u;
             }
         }
         return h;
@@ -160,15 +170,19 @@ struct CollideGrid {
  * loop-invariant (the reference recomputes it every step, :36); v / L is exact for L = 1. */
 struct DynParams { float W, H, L; int numDisc; };
 
+struct EdgeWork { unsigned steps, pairs; };   /* loop trips of statePropagator.cu:31 executed, overlap tests executed */
+
 template <class Collide>
-__device__ __forceinline__ bool propagate_edge(float4& s, const Controls& u, const DynParams& p, const Collide& col) {
+__device__ __forceinline__ bool propagate_edge(float4& s, const Controls& u, const DynParams& p, const Collide& col,
+                                               EdgeWork* work = nullptr) {
     const float dt = __fdiv_rn(u.duration, (float)p.numDisc);
     const float tanS = tanf(u.steering);
     const bool unitL = (p.L == 1.0f);
     float x = s.x, y = s.y, th = s.z, v = s.w;
     typename Collide::Cursor cur = col.start(x, y);
     bool valid = true;
-    for (int i = 0; i < p.numDisc; ++i) {
+    int i = 0;
+    for (; i < p.numDisc; ++i) {
         const float px = x, py = y;
         float sn, cs;
         sincosf(th, &sn, &cs);      /* one range reduction; bit-identical to sinf(th), cosf(th) (checked against the reference's kernels) */
@@ -182,6 +196,7 @@ __device__ __forceinline__ bool propagate_edge(float4& s, const Controls& u, con
         const float bny = (py > y) ? y : py, bxy = (py > y) ? py : y;
         if (col.hit(cur, x, y, bnx, bny, bxx, bxy)) { valid = false; break; }
     }
+    if (work) { work->steps = (unsigned)(valid ? p.numDisc : i + 1); work->pairs = cur.pairs; }
     s = make_float4(x, y, th, v);
     return valid;
 }
@@ -199,7 +214,7 @@ __device__ __forceinline__ void edge_tile_pass(const float4 s0, const Controls& 
                                                const float4* tile, int nObs, EdgeExit& e) {
     const bool unitL = (p.L == 1.0f);
     const CollideSmemAll col{tile, nObs};
-    CollideSmemAll::Cursor cur;
+    CollideSmemAll::Cursor cur{0u};
     float x = s0.x, y = s0.y, th = s0.z, v = s0.w;
     const int limit = FIRST ? p.numDisc : e.step;
     for (int i = 0; i < limit; ++i) {

@@ -42,6 +42,7 @@ ABI_SYMBOLS = [
     "kgmt_set_stream", "kgmt_shard_delta_ints", "kgmt_shard_expand", "kgmt_shard_pack", "kgmt_shard_commit",
     "kgmt_peer_handle_bytes", "kgmt_peer_export", "kgmt_peer_attach", "kgmt_peer_attach_local", "kgmt_peer_expand_begin",
     "kgmt_peer_expand_end", "kgmt_peer_detach", "kgmt_peer_race",
+    "kgmt_params_from_yaml", "kgmt_stage_update_maps", "kgmt_stage_insert", "kgmt_work_counters",
 ]
 
 
@@ -54,7 +55,9 @@ class Params(C.Structure):
                 ("num_iterations", C.c_int), ("max_tree_size", C.c_int), ("num_disc", C.c_int),
                 ("agent_length", C.c_float), ("goal_threshold", C.c_float), ("seed", C.c_uint32),
                 ("device", C.c_int), ("max_candidates", C.c_int), ("collision_mode", C.c_int),
-                ("record_candidates", C.c_int), ("cull_cells", C.c_int), ("reserved", C.c_int * 5)]
+                ("record_candidates", C.c_int), ("cull_cells", C.c_int), ("reserved", C.c_int * 5),
+                ("accel_min", C.c_double), ("accel_max", C.c_double), ("steer_min", C.c_double),
+                ("steer_max", C.c_double), ("duration_min", C.c_double), ("duration_max", C.c_double)]
 
 
 class IterStats(C.Structure):
@@ -154,6 +157,10 @@ def load():
     L.kgmt_peer_expand_end.argtypes = [vp, C.POINTER(IterStats)]
     L.kgmt_peer_detach.argtypes = [vp]
     L.kgmt_peer_race.argtypes = [vp, f32p, f32p, C.c_int, C.POINTER(Result)]
+    L.kgmt_params_from_yaml.argtypes = [C.c_char_p, C.POINTER(Params), C.POINTER(C.c_int)]
+    L.kgmt_stage_update_maps.argtypes = [vp, f32p, C.POINTER(C.c_ubyte), f32p, C.POINTER(C.c_int), C.c_int]
+    L.kgmt_stage_insert.argtypes = [vp, C.POINTER(IterStats)]
+    L.kgmt_work_counters.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     _lib = L
     return L
 
@@ -182,7 +189,7 @@ class KGMT:
     def __init__(self, width=20.0, height=20.0, N=16, n=8, numIterations=100, maxTreeSize=30000, numDisc=10,
                  agentLength=1.0, goalThreshold=0.5, *, seed=1, device=-1, max_candidates=0,
                  collision_mode=COLLIDE_GRID, record_candidates=False, cull_cells=0, stage_limit_bytes=0,
-                 ctas_per_sm=0, loop=0):
+                 ctas_per_sm=0, chunks_in_flight=0, car=None, car_yaml=None):
         L = load()
         p = default_params()
         p.width, p.height, p.N, p.n = width, height, N, n
@@ -192,7 +199,15 @@ class KGMT:
         p.collision_mode, p.record_candidates, p.cull_cells = collision_mode, int(bool(record_candidates)), cull_cells
         p.reserved[0] = stage_limit_bytes
         p.reserved[1] = ctas_per_sm          # 0 = as many as fit
-        p.reserved[2] = loop                 # planner loop: 0 default, 1 barrier-free pipelined, 2 grid barrier
+        p.reserved[2] = chunks_in_flight     # 32-candidate chunks a warp keeps in flight per pass of phase A (0 = default)
+        if car_yaml is not None:             # systems/car.yaml-style model file (flat key: value; empty = defaults)
+            bad = C.c_int(0)
+            if L.kgmt_params_from_yaml(os.fsencode(car_yaml), C.byref(p), C.byref(bad)) != OK:
+                raise KgmtError("cannot read car model %s (line %d)" % (car_yaml, bad.value))
+        for key, val in (car or {}).items():  # accel_min/max, steer_min/max, duration_min/max
+            if key not in ("accel_min", "accel_max", "steer_min", "steer_max", "duration_min", "duration_max"):
+                raise KgmtError("unknown car model key %r" % key)
+            setattr(p, key, float(val))
         self.params = p
         self.N, self.n, self.max_tree = N, n, maxTreeSize
         self.max_cand = max_candidates if max_candidates > 0 else maxTreeSize
@@ -322,6 +337,33 @@ class KGMT:
         self._ck(load().kgmt_stage_propagate(self._h, a.ctypes.data_as(C.POINTER(C.c_float)), a.shape[0], int(children),
                                              int(key0) & 0xFFFFFFFF, int(slot0) & 0xFFFFFFFF, C.byref(ms)))
         return ms.value
+
+    def stage_update_maps(self, cand7, valid, u3, parent):
+        """Stage 5a alone on caller-supplied candidates (needs record_candidates=True and a begun context)."""
+        c = _f32(cand7).reshape(-1, 7)
+        M = len(c)
+        v = np.ascontiguousarray(valid, dtype=np.uint8)
+        u = _f32(u3, M)
+        pa = np.ascontiguousarray(parent, dtype=np.int32)
+        if v.size != M or pa.size != M:
+            raise ValueError("valid / parent must have one entry per candidate")
+        self._ck(load().kgmt_stage_update_maps(self._h, c.ctypes.data_as(C.POINTER(C.c_float)),
+                                               v.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                                               u.ctypes.data_as(C.POINTER(C.c_float)),
+                                               pa.ctypes.data_as(C.POINTER(C.c_int)), M))
+
+    def stage_insert(self):
+        """Stage 5b alone: ordered insertion of what stage_update_maps accepted; returns the iteration stats."""
+        st = IterStats()
+        self._ck(load().kgmt_stage_insert(self._h, C.byref(st)))
+        self.treeSize_, self.costToGoal_ = st.tree_size, st.cost_to_goal
+        return st.as_dict()
+
+    def work_counters(self):
+        """{steps, pairs, expansions} executed by the recording kernels since the plan began."""
+        out = (C.c_ulonglong * 4)()
+        self._ck(load().kgmt_work_counters(self._h, out))
+        return {"steps": int(out[0]), "pairs": int(out[1]), "expansions": int(out[2])}
 
     def extract_path(self, node=-1, max_rows=4096):
         buf = np.zeros((max_rows, 7), dtype=np.float32)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define KGMT_ABI_VERSION 1
+#define KGMT_ABI_VERSION 2
 #define KGMT_SAMPLE_DIM 7            /* (x, y, theta, v, a, steering, duration): KGMT.cu:5, State.h:9-20 */
 
 typedef enum kgmt_status {
@@ -70,7 +70,19 @@ typedef struct kgmt_params {
     int      cull_cells;             /* cull grid is cull_cells x cull_cells; 0 = choose from the obstacle set */
     int      reserved[5];            /* [0]: shared-memory staging budget for the collision data in bytes (0 = 60 KB);
                                         [1]: resident CTAs per SM of the persistent kernel (0 = all that fit);
-                                        [2]: planner loop, 0 = default, 1 = barrier-free pipelined, 2 = grid barrier; rest 0 */
+                                        [2]: candidates a warp keeps in flight per pass of phase A, in chunks of 32
+                                             (0 = default); rest 0 */
+    /* The car model ("systems/car.yaml" of the reference is an empty file; its dynamics and control ranges are literals
+     * in statePropagator.cu:17-19).  Control c is drawn as lo + u * (hi - lo), u = curand_uniform in (0, 1]:
+     *   a        = fmaf(u0, (float)(accel_max - accel_min), (float)accel_min)              :17  u0 * 10.0f - 5.0f
+     *   steering = (float) fma((double)u1, steer_max - steer_min, steer_min)               :18  u1 * 2.0f * M_PI - M_PI
+     *   duration = fmaf(u2, (float)(duration_max - duration_min), (float)duration_min)     :19  u2 * 1.0f + 0.05f
+     * With the defaults (kgmt_default_params) these are bit for bit the reference's expressions as nvcc compiles them
+     * for sm_100a (one FFMA; one DFMA on (double)(u1+u1) == 2*(double)u1; u2 * 1 + 0.05f).  Doubles because the
+     * reference's steering bounds are the double constant M_PI. */
+    double   accel_min, accel_max;           /* default -5, 5 */
+    double   steer_min, steer_max;           /* default -M_PI, M_PI */
+    double   duration_min, duration_max;     /* default (double)0.05f, (double)0.05f + 1 */
 } kgmt_params;
 
 typedef struct kgmt_iter_stats {
@@ -130,7 +142,14 @@ typedef struct kgmt_ctx kgmt_ctx;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
 int  kgmt_abi_version(void);
-void kgmt_default_params(kgmt_params* p);                       /* main.cu:19-28 literals */
+void kgmt_default_params(kgmt_params* p);                       /* main.cu:19-28 literals + statePropagator.cu:17-19 control ranges */
+/* Overlay `p` (already holding defaults or the caller's values) with the keys found in a car-model file in the
+ * reference's systems/ directory (systems/car.yaml is EMPTY upstream: an empty or missing-key file changes nothing).
+ * Flat "key: value" YAML subset, '#' comments, optional one-level nesting ("controls:" / "planner:" blocks are
+ * flattened).  Keys: wheelbase | agent_length, num_disc, accel_min, accel_max, steer_min, steer_max, duration_min,
+ * duration_max, width, height, N, n, num_iterations, max_tree_size, goal_threshold, seed.  Unknown keys are an error
+ * (KGMT_ERR_INVALID; *bad_line receives the 1-based line number when not NULL). */
+int  kgmt_params_from_yaml(const char* path, kgmt_params* p, int* bad_line);
 int  kgmt_create(const kgmt_params* p, kgmt_ctx** out);         /* replaces KGMT::KGMT, KGMT.cu:10-78 */
 void kgmt_destroy(kgmt_ctx* ctx);                               /* replaces ~KGMT + KGMT.cu:314-316 */
 const char* kgmt_last_error(const kgmt_ctx* ctx);               /* replaces CUDA_ERROR_CHECK's printf, helper.cuh:19-27 */
@@ -221,6 +240,18 @@ int  kgmt_stage_scores(kgmt_ctx* ctx);
  * (propagateAndCheck, statePropagator.cu:5-76 + getR1/getR2, KGMT.cu:602-629) */
 int  kgmt_stage_propagate(kgmt_ctx* ctx, const float* h_parents7, int P, int children,
                           uint32_t key0, uint32_t slot0, float* device_ms);
+/* Stage 5a alone on CALLER-SUPPLIED candidates (tail of propagateG / propagateGV2, KGMT.cu:390-411 / :458-480): the M
+ * candidates (HOST: rows of 7 floats as the reference's unexploredSamples, valid flags 0/1, accept uniforms, parent tree
+ * indices) replace the pending iteration's candidates: region indices, R1/R2 counters, accept test against the CURRENT
+ * maps and scores (set them with kgmt_import) on the iteration-start snapshot, ballots and staging for the insertion.
+ * The per-candidate results are exported as KGMT_ARR_U_R1 / U_R2 / U_ACCEPT; needs record_candidates = 1 and a begun
+ * context (kgmt_begin / kgmt_seed_frontier); M <= max_candidates. */
+int  kgmt_stage_update_maps(kgmt_ctx* ctx, const float* h_cand7, const unsigned char* h_valid, const float* h_u3,
+                            const int* h_parent, int M);
+/* Stage 5b alone (scan(GNew) + findInd + updateG, KGMT.cu:222-245, :540-593, then :249-259): ordered insertion of the
+ * candidates accepted by the preceding kgmt_stage_update_maps, parent links from its h_parent, cost = cost[parent] +
+ * duration, goal test; advances the planner scalars and scores the next iteration. */
+int  kgmt_stage_insert(kgmt_ctx* ctx, kgmt_iter_stats* out);
 /* Load `count` nodes (HOST rows of 7 floats) as tree[0,count), all of them frontier, costs 0, root cells
  * marked like KGMT.cu:88-97 for every node; then kgmt_expand_iteration steps from there. */
 int  kgmt_seed_frontier(kgmt_ctx* ctx, const float* h_nodes7, int count, const float* goal7);
@@ -245,6 +276,11 @@ float kgmt_r1_size(const kgmt_ctx* ctx);                         /* KGMT::R1Size
 float kgmt_r2_size(const kgmt_ctx* ctx);                         /* KGMT::R2Size_, KGMT.cu:14 */
 void* kgmt_stream(const kgmt_ctx* ctx);                          /* cudaStream_t the context launches on */
 long long kgmt_launch_count(const kgmt_ctx* ctx);                /* kernels of this library launched so far */
+/* work done by the recording kernels (record_candidates = 1) since the last kgmt_begin / kgmt_plan / kgmt_seed_frontier:
+ * out4 = {Euler steps executed (statePropagator.cu:31 loop trips), (step bbox, obstacle AABB) overlap tests executed
+ * (collisionCheck.cu:6-14 calls; with the culled back end: entries read from the cell lists, padding included),
+ * candidate edges, 0}.  The non-recording kernels do not count (the counters cost instructions). */
+int  kgmt_work_counters(kgmt_ctx* ctx, unsigned long long* out4);
 /* diagnostics: enable != 0 turns on per-iteration device timestamps; out8 rows (8 x u64) = {globaltimer ns when the
  * iteration was finalized, candidates << 32 | accepted, then CTA 0's globaltimer at: iteration start, phase A done,
  * first grid barrier passed, phase B done, last grid barrier passed, 0} of the last plan; returns rows written */

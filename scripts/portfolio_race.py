@@ -13,7 +13,7 @@ if world > 1: dist.init_process_group("nccl", device_id=torch.device("cuda", loc
 races = int(sys.argv[1]) if len(sys.argv) > 1 else 101
 race_id = 0
 for name, cfg, obs, init, goal in (("c1", w.C1, w.C1_OBSTACLES, w.C1_INIT, w.C1_GOAL), ("c2", w.C2, w.c2_obstacles(1000), w.C2_INIT, w.C2_GOAL)):
-    p = K.KGMT(**cfg, seed=1, device=local, loop=2); p.set_obstacles(obs)
+    p = K.KGMT(**cfg, seed=1, device=local); p.set_obstacles(obs)
     ex = PeerExpander(p)                                   # exchanges the cudaIpc handles, attaches
     rows = []
     for q in range(races + 3):

@@ -36,11 +36,39 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_abi_version_and_defaults(lib):
     import cudasbmp_b200 as k
-    assert lib.kgmt_abi_version() == 1
+    assert lib.kgmt_abi_version() == 2
     p = k.kgmt.default_params()
     # demos/main.cu:19-28
     assert (p.width, p.height, p.N, p.n, p.num_iterations, p.max_tree_size, p.num_disc) == (20.0, 20.0, 16, 8, 100, 30000, 10)
     assert (p.agent_length, p.goal_threshold) == (1.0, 0.5)
+    # statePropagator.cu:17-19: a in (-5, 5], steering in (-pi, pi], duration in (0.05, 1.05]
+    import math
+    import numpy as np
+    assert (p.accel_min, p.accel_max, p.steer_min, p.steer_max) == (-5.0, 5.0, -math.pi, math.pi)
+    assert p.duration_min == float(np.float32(0.05)) and p.duration_max == float(np.float32(0.05)) + 1.0
+
+
+def test_car_yaml_loader(lib, tmp_path):
+    """systems/car.yaml of the reference is an EMPTY file: loading it must leave the defaults; a populated file
+    overrides exactly its keys; unknown keys are reported with their line."""
+    import cudasbmp_b200 as k
+    empty = tmp_path / "car.yaml"
+    empty.write_text("")
+    p = k.kgmt.default_params()
+    bad = C.c_int(-1)
+    assert lib.kgmt_params_from_yaml(os.fsencode(str(empty)), C.byref(p), C.byref(bad)) == 0
+    d = k.kgmt.default_params()
+    assert all(getattr(p, f) == getattr(d, f) for f, _ in p._fields_ if f != "reserved")
+    full = tmp_path / "car2.yaml"
+    full.write_text("# kinematic bicycle\nwheelbase: 2.5\ncontrols:\n  accel_min: -3\n  accel_max: 2.5  # m/s^2\n"
+                    "  steer_min: -0.25pi\n  steer_max: 0.5\n  duration_min: 0.1\n  duration_max: 0.6\nnum_disc: 20\n")
+    assert lib.kgmt_params_from_yaml(os.fsencode(str(full)), C.byref(p), C.byref(bad)) == 0
+    import math
+    assert (p.agent_length, p.num_disc, p.accel_min, p.accel_max) == (2.5, 20, -3.0, 2.5)
+    assert (p.steer_min, p.steer_max, p.duration_min, p.duration_max) == (-0.25 * math.pi, 0.5, 0.1, 0.6)
+    wrong = tmp_path / "car3.yaml"
+    wrong.write_text("wheelbase: 1\nturbo: 9\n")
+    assert lib.kgmt_params_from_yaml(os.fsencode(str(wrong)), C.byref(p), C.byref(bad)) == -1 and bad.value == 2
 
 
 def test_no_cpu_fallback(lib):

@@ -359,40 +359,6 @@ def test_c3_streamed_tiles_equal_grid(K_obs, limit, backend):
     assert rb2["tree_size"] == rb["tree_size"] and _tree_checksum(b, rb2["tree_size"]) == _tree_checksum(a, ra["tree_size"])
 
 
-@pytest.mark.parametrize("cfgname", ["c1", "c2"])
-def test_pipelined_loop_equals_barrier_loop(cfgname):
-    """The barrier-free planner loop (progressive ordered insertion by idle warps, one speculative chunk of the next
-    iteration per warp, cooperative scores) builds exactly what the grid-barrier loop builds: tree, links, costs, maps,
-    scores, goal node; whole plans and host-stepped iterations alike."""
-    if cfgname == "c1":
-        cfg, obs, init, goal = w.C1, w.C1_OBSTACLES, w.C1_INIT, w.C1_GOAL
-    else:
-        cfg, obs, init, goal = w.C2, w.c2_obstacles(1000), w.C2_INIT, w.C2_GOAL
-    maps = (K.ARR_R1, K.ARR_R1VALID, K.ARR_R1INVALID, K.ARR_R1AVAIL, K.ARR_R2, K.ARR_R2VALID, K.ARR_R2INVALID,
-            K.ARR_R2AVAIL, K.ARR_R1SCORE)
-    a = _plan(cfg, obs, seed=4, loop=2)
-    b = _plan(cfg, obs, seed=4, loop=1)
-    for seed in (4, 5, 6):
-        a.set_seed(seed); b.set_seed(seed)
-        ra, rb = a.plan(init, goal), b.plan(init, goal)
-        for k in ("stop", "iterations", "tree_size", "expansions", "cost_to_goal", "goal_index"):
-            assert ra[k] == rb[k], (seed, k, ra[k], rb[k])
-        assert _tree_checksum(a, ra["tree_size"]) == _tree_checksum(b, rb["tree_size"])
-        for m in maps:
-            assert (a.export(m).view(np.uint32) == b.export(m).view(np.uint32)).all(), m
-        if ra["stop"] == 1:
-            np.testing.assert_array_equal(a.extract_path(), b.extract_path())
-    # stepwise: 1 iteration per launch, then 3 per launch, on the pipelined loop
-    c = _plan(cfg, obs, seed=6, loop=1)
-    c.begin(init, goal)
-    c.iterate(); c.iterate()
-    while c.iterate_many(3)["stop"] == 0:
-        pass
-    rc = c.result()
-    assert (rc["tree_size"], rc["iterations"], rc["stop"], rc["expansions"]) == (ra["tree_size"], ra["iterations"], ra["stop"], ra["expansions"])
-    assert _tree_checksum(c, rc["tree_size"]) == _tree_checksum(a, ra["tree_size"])
-
-
 def test_csv_dump_matches_reference_format(tmp_path):
     """The 13 files of KGMT.cu:299-311 in the format of helper.cuh:53-72 ("%.10f", one row per node)."""
     plan = _plan(dict(w.C1, maxTreeSize=2000), w.C1_OBSTACLES, record_candidates=True, seed=3)

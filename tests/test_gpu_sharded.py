@@ -162,8 +162,8 @@ def test_peer_portfolio_race_flag():
     the word set for the current race stops at its next iteration boundary with stop == 5 (peer solved).  Two contexts of
     this process take turns (two cooperative launches cannot share one GPU), which makes the outcome deterministic."""
     cfg, obs = w.C1, w.C1_OBSTACLES
-    a = K.KGMT(**cfg, seed=3, loop=2); a.set_obstacles(obs)          # the race lives in the grid-barrier loop
-    b = K.KGMT(**cfg, seed=4, loop=2); b.set_obstacles(obs)
+    a = K.KGMT(**cfg, seed=3); a.set_obstacles(obs)          # the race lives in the grid-barrier loop
+    b = K.KGMT(**cfg, seed=4); b.set_obstacles(obs)
     ref = K.KGMT(**cfg, seed=3); ref.set_obstacles(obs)
     want = ref.plan(w.C1_INIT, w.C1_GOAL)
     a.peer_attach_local(0, [a, b]); b.peer_attach_local(1, [a, b])
