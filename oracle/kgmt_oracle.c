@@ -79,8 +79,34 @@ void orc_slot_uniforms(uint32_t key0, uint32_t slot, float u[4]) {
 }
 
 /* -------------------------------------------------------------- controls -- */
+/* Control ranges other than the reference's literals (kgmt_params accel/steer/duration min..max; the reference's
+ * systems/car.yaml is empty and statePropagator.cu:17-19 hard-codes them).  Process-global, test infrastructure:
+ * orc_set_car_ranges(NULL) restores the literal path below, which is the one pinned against the reference build.
+ * The general form is lo + u * (hi - lo) with the same operation shapes: float for a and duration, double for the
+ * steering (the reference multiplies by the double constant M_PI). */
+static int g_car_set = 0;
+static double g_car[6];
+void orc_set_car_ranges(const double* r6) {
+    g_car_set = r6 != NULL;
+    if (r6) memcpy(g_car, r6, sizeof(g_car));
+}
+void orc_controls_general(const float u[3], const double r[6], int math_mode, float* a, float* steering, float* duration) {
+    const float aS = (float)(r[1] - r[0]), aL = (float)r[0], dS = (float)(r[5] - r[4]), dL = (float)r[4];
+    const double sS = r[3] - r[2], sL = r[2];
+    if (math_mode == ORC_MATH_FMA) {
+        *a = fmaf(u[0], aS, aL);
+        *steering = (float)fma((double)u[1], sS, sL);
+        *duration = fmaf(u[2], dS, dL);
+    } else {
+        volatile float ta = u[0] * aS;  *a = ta + aL;
+        volatile double ts = (double)u[1] * sS;  *steering = (float)(ts + sL);
+        volatile float td = u[2] * dS;  *duration = td + dL;
+    }
+}
+
 /* src/statePropagator/statePropagator.cu:17-19 */
 void orc_controls(const float u[3], int math_mode, float* a, float* steering, float* duration) {
+    if (g_car_set) { orc_controls_general(u, g_car, math_mode, a, steering, duration); return; }
     if (math_mode == ORC_MATH_FMA) {
         *a = fmaf(u[0], 10.0f, -5.0f);
         *steering = (float)fma((double)(u[1] * 2.0f), M_PI, -M_PI);

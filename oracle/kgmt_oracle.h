@@ -36,6 +36,9 @@ void  orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t o
 float orc_uniform(uint32_t x);
 void  orc_slot_uniforms(uint32_t key0, uint32_t slot, float u[4]);
 void  orc_controls(const float u[3], int math_mode, float* a, float* steering, float* duration);
+/* control ranges {accel_min, accel_max, steer_min, steer_max, duration_min, duration_max}; NULL = the reference's literals */
+void  orc_set_car_ranges(const double* r6);
+void  orc_controls_general(const float u[3], const double r[6], int math_mode, float* a, float* steering, float* duration);
 int   orc_motion_valid(const float bbMin[2], const float bbMax[2], const float* obstacles, int K);
 int   orc_propagate_ctrl(const float x0[4], float a, float steering, float duration,
                          int numDisc, float agentLength, const float* obstacles, int K,

@@ -108,6 +108,12 @@ def lib():
         L.orc_philox4x32_10.argtypes = [u32p, u32p, u32p]
         L.orc_slot_uniforms.restype = None
         L.orc_slot_uniforms.argtypes = [C.c_uint32, C.c_uint32, f32p]
+        L.orc_set_car_ranges.restype = None
+        L.orc_set_car_ranges.argtypes = [C.POINTER(C.c_double)]
+        L.orc_controls.restype = None
+        L.orc_controls.argtypes = [f32p, C.c_int, f32p, f32p, f32p]
+        L.orc_controls_general.restype = None
+        L.orc_controls_general.argtypes = [f32p, C.POINTER(C.c_double), C.c_int, f32p, f32p, f32p]
         L.orc_in_goal.restype = C.c_int
         L.orc_in_goal.argtypes = [f32p, f32p, C.c_float]
         _lib = L
@@ -115,6 +121,27 @@ def lib():
 
 
 # ----------------------------------------------------------------------------- small helpers
+def set_car_ranges(r6=None):
+    """Control ranges (accel_min, accel_max, steer_min, steer_max, duration_min, duration_max) for every later
+    orc_* call of this process; None restores the reference's literals (statePropagator.cu:17-19)."""
+    if r6 is None:
+        lib().orc_set_car_ranges(None)
+    else:
+        lib().orc_set_car_ranges((C.c_double * 6)(*[float(v) for v in r6]))
+
+
+def controls(u3, math_mode=MATH_FMA, ranges=None):
+    """(a, steering, duration) from three uniforms: the literal path, or the general one when ranges is given."""
+    u = np.ascontiguousarray(u3, dtype=np.float32)
+    a, s, d = C.c_float(), C.c_float(), C.c_float()
+    if ranges is None:
+        lib().orc_controls(_p(u, f32p), math_mode, C.byref(a), C.byref(s), C.byref(d))
+    else:
+        lib().orc_controls_general(_p(u, f32p), (C.c_double * 6)(*[float(v) for v in ranges]), math_mode,
+                                   C.byref(a), C.byref(s), C.byref(d))
+    return a.value, s.value, d.value
+
+
 def philox(ctr, key):
     c = np.asarray(ctr, dtype=np.uint32)
     k = np.asarray(key, dtype=np.uint32)

@@ -262,6 +262,43 @@ def test_edge_cases(oracle):
         plan.iterate()
 
 
+def test_iteration_shape_never_exceeds_tree_or_candidate_capacity():
+    """forced children persist across iterations and max_candidates may be smaller than the tree; neither may
+    produce an iteration that overruns the candidate staging or the tree (expansion_shape clamps to both)."""
+    obs = w.C1_OBSTACLES
+    # forced children, several iterations in one launch: falls back to the reference policy once 8 per node no longer fit
+    plan = _plan(dict(w.C1, maxTreeSize=6000, numIterations=30), obs, record_candidates=True, seed=3)
+    nodes = w.random_parents(64, obs, seed=3)
+    plan.seed_frontier(nodes, w.C1_GOAL)
+    plan.set_children(8)
+    seen = []
+    for _ in range(30):
+        st = plan.iterate()
+        seen.append((st["mode"], st["children"], st["candidates"], st["tree_size"]))
+        assert st["candidates"] <= 6000 and st["tree_size"] <= 6000, seen
+        if st["stop"] != 0:
+            break
+    assert seen[0][0] == 4 and seen[0][1] == 8
+    plan.set_children(0)
+    # the same through the multi-iteration launch
+    plan2 = _plan(dict(w.C1, maxTreeSize=6000, numIterations=30), obs, seed=3)
+    plan2.seed_frontier(nodes, w.C1_GOAL)
+    plan2.set_children(8)
+    st2 = plan2.iterate_many(30)
+    assert st2["tree_size"] == seen[-1][3] and plan2.result()["iterations"] == len(seen)
+    # a candidate staging smaller than the tree: every iteration fits it, the plan still runs to a regular stop
+    small = _plan(dict(w.C1), obs, record_candidates=True, seed=4, max_candidates=2048)
+    small.begin(w.C1_INIT, w.C1_GOAL)
+    for _ in range(100):
+        st = small.iterate()
+        assert st["candidates"] <= 2048 and st["tree_size"] <= 30000, st
+        if st["stop"] != 0:
+            break
+    assert st["stop"] in (1, 2, 3, 4)
+    r = _plan(dict(w.C1), obs, seed=4, max_candidates=2048).plan(w.C1_INIT, w.C1_GOAL)
+    assert (r["tree_size"], r["stop"]) == (st["tree_size"], st["stop"])
+
+
 # ------------------------------------------------------------------------------------ whole-plan properties
 def _tree_checksum(plan, T):
     h = zlib.crc32(plan.export(K.ARR_SAMPLES)[:T].tobytes())

@@ -119,3 +119,21 @@ def test_live_reference_host_build(oracle):
     x1, v, u3, _ = oracle.propagate_batch(par, pof, 4242, 100, 10, 1.0, obs, 20.0, 20.0, oracle.MATH_HOST)
     _, rx, rv, ru = oracle.ref_host_batch(par, pof, 4242, 100, 10, 1.0, obs, 20.0, 20.0)
     assert (x1.view(np.uint32) == rx.view(np.uint32)).all() and (v == rv).all() and (u3 == ru).all()
+
+
+def test_general_control_ranges_equal_the_literals_at_the_defaults(oracle):
+    """The product draws controls as lo + u * (hi - lo) from kgmt_params (runtime car model); the oracle restates that
+    general form next to the reference's literal expressions (statePropagator.cu:17-19, pinned above against the
+    reference's own host build).  At the default ranges the two must agree bit for bit, in both math modes, for random
+    uniforms and for the extremes of curand_uniform's range (2^-33 and 1)."""
+    import math
+    d = [-5.0, 5.0, -math.pi, math.pi, float(np.float32(0.05)), float(np.float32(0.05)) + 1.0]
+    rng = np.random.default_rng(1)
+    words = list(rng.integers(0, 2 ** 32, 30000, dtype=np.uint64)) + [0, 1, 2 ** 32 - 1, 2 ** 31, 2 ** 31 - 1]
+    L = oracle.lib()
+    for i in range(0, len(words) - 2, 3):
+        u = np.array([L.orc_uniform(int(words[i + j])) for j in range(3)], dtype=np.float32)
+        for mode in (oracle.MATH_FMA, oracle.MATH_HOST):
+            a = np.array(oracle.controls(u, mode), dtype=np.float32)
+            b = np.array(oracle.controls(u, mode, d), dtype=np.float32)
+            assert a.tobytes() == b.tobytes(), (u, mode, a, b)
