@@ -1,19 +1,31 @@
 #!/usr/bin/env python
 """bench.py — checked edge expansions/sec of the KGMT tree-expansion path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--skip c3,c4,c5,ttfs,...]
 
-A step = one complete KGMT plan (root insertion + every expansion iteration until the goal is reached, the tree is
-full or the iteration limit hits) of BASELINE config 2: car, synthetic dense map of 1 000 obstacle AABBs,
-2^20-node tree capacity, N=16 / n=32 region grid, step s planned with seed s+1.  One process per GPU; with N > 1 the
-seeds (independent planning queries) are sharded over the ranks, no data-path collective (weak scaling).
+Headline (every N): BASELINE config 2 — car, synthetic dense map of 1 000 obstacle AABBs, 2^20-node tree capacity,
+N=16 / n=32 region grid.  A STEP = one batch of PLANS_PER_STEP complete KGMT plans (root insertion + every expansion
+iteration until the goal is reached, the tree is full or the iteration limit hits), plan j of step s planned with its
+own seed.  One process per GPU; with N > 1 the seeds (independent planning queries) are sharded over the ranks, no
+data-path collective (weak scaling).
 
-  value   total expansions of the K timed plans / their device time (CUDA events on the planner's stream around
-          reset + root kernel + the cooperative expansion kernel; obstacles, cull grid and tree storage resident in HBM)
-  e2e     the same plans through the public C-ABI calls with HOST buffers every step: kgmt_set_obstacles_host
-          (H2D of the obstacle set + cull grid) + kgmt_plan (host init/goal) + result block and solution path D2H,
-          wall clock between device synchronisations
-  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement".
+  value   total expansions of the timed plans / their device time (CUDA events on the planner's stream around
+          reset + root kernel + the cooperative expansion kernel; obstacles, cull grid and tree storage resident in
+          HBM; L2 flushed before every plan, outside the events)
+  e2e     the same plans through the public C-ABI calls with HOST buffers: kgmt_set_obstacles_host (H2D of the
+          obstacle set + cull grid) + kgmt_plan (host init/goal) + result block and solution path D2H, wall clock
+          between device synchronisations
+  roofline / roofline_issue / roofline_fp32 / cpu_baseline / clocks / gpu_launches: DESIGN.md "Measurement".
+
+Further keys of the same JSON line measure the other named configurations (VERDICT r01 "next" 2):
+  ttfs        median time-to-first-solution on config 1 and config 2 (101 seeds), and — N = 1 — the reference's own
+              plan() on config 1 (ttfs.reference_ms)
+  ttfs_multi  N > 1: the same as a portfolio race over peer memory (one seed per GPU, first solution stops the rest)
+  c3          N = 1: config 3 (10 000 obstacles, numDisc 40) with the culled and the TMA-streamed exhaustive back end
+  c4          config 4: the FIXED batch of 1 024 queries sharded over the N ranks (strong scaling), kgmt_plan_batch
+  c5          config 5: one sharded iteration of M = 2^20 .. 2^26 candidates, compute and exchange time
+  same_population   stages 2-4 on IDENTICAL inputs (frontier nodes sampled from a real config-2 plan x 32 children,
+              same Philox streams): this library, the reference's CUDA kernel, the reference's host loop
 
 --impl reference times the reference's OWN propagate+collision loop (oracle/_ref/libref_host.so: its unmodified
 statePropagator.cu + collisionCheck.cu built for the host) on all host cores, on a bounded sample of the same workload.
@@ -35,6 +47,8 @@ sys.path.insert(0, ROOT)
 METRIC = "checked edge expansions/sec"
 UNIT = "expansions/s"
 B_EXP, B_INS = 33.5, 77.0          # algorithmic HBM bytes per expansion / per accepted node
+PLANS_PER_STEP = 64                # a step = one batch of this many complete plans (>= 1 s timed at the driver's 20 steps)
+SAMPLE = os.path.join(ROOT, "bench_data", "c2_frontier_sample.npz")
 
 
 def workload(name):
@@ -47,6 +61,18 @@ def workload(name):
                     label="config3: car, 10000 synthetic AABBs, numDisc=40, N=16 n=32, maxTree=2^20")
     return dict(cfg=w.C2, obstacles=w.c2_obstacles(1000), init=w.C2_INIT, goal=w.C2_GOAL,
                 label="config2: car KGMT single query, 1000 synthetic AABBs, N=16 n=32, maxTree=2^20, numDisc=10")
+
+
+def sample_parents(wl):
+    """Parents of the bounded samples: frontier nodes of a REAL config-2 plan (bench_data/, made on a B200 by
+    scripts/dump_frontier_sample.py) — the same candidate population the GPU arm expands; free-space random parents
+    only when the fixture is missing or for another map."""
+    from cudasbmp_b200 import workloads as w
+    if wl["label"].startswith("config2") and os.path.exists(SAMPLE):
+        d = np.load(SAMPLE)
+        return np.ascontiguousarray(d["parents"], dtype=np.float32), "frontier nodes of a config-2 plan (seed %d, iterations %s)" % (
+            int(d["seed"]), ",".join(str(int(i)) for i in d["iterations"]))
+    return w.random_parents(4096, wl["obstacles"], seed=7), "random free-space parents"
 
 
 class ClockSampler:
@@ -80,29 +106,41 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
-                sm.append(float(r[1])); smax.append(float(r[2]))
+                sm.append(float(r[1])); smax.append(float(r[2])); pw.append(float(r[3]))
                 for nm, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
             except Exception:
                 pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_mhz_min": min(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "power_w_max": max(pw) if pw else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_cpu():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return model, os.cpu_count() or 1
 
 
 def cpu_reference_rate(wl, seconds=12.0, threads=None):
     """The reference's own propagate+collision loop (host build) on a bounded sample of the workload."""
     from oracle import pyoracle as po
-    from cudasbmp_b200 import workloads as w
     R = po.ref_host()
     kind = "reference"
     cfg, obs = wl["cfg"], wl["obstacles"]
     cores = threads or (R.ref_host_hw_threads() if R is not None else (os.cpu_count() or 1))
-    parents = w.random_parents(4096, obs, seed=7)
+    parents, what = sample_parents(wl)
 
     def run(M):
         pof = (np.arange(M, dtype=np.int32) // 32) % len(parents)
@@ -123,34 +161,312 @@ def cpu_reference_rate(wl, seconds=12.0, threads=None):
     rate = M / max(sec, 1e-9)
     M2 = int(min(max(rate * seconds, M), 64e6)) // 32 * 32
     sec2 = run(M2)
-    return dict(value=M2 / sec2, unit=UNIT, cores=cores, kind=kind,
-                sample="%d candidate edges from 4096 free-space parents x 32 children on the %s map, %.1f s wall"
-                       % (M2, wl["label"].split(":")[0], sec2)), M2, sec2
+    model, ncpu = host_cpu()
+    return dict(value=M2 / sec2, unit=UNIT, cores=cores, kind=kind, host_cpu=model, host_logical_cpus=ncpu,
+                sample="%d candidate edges = %s x 32 children on the %s map, %.1f s wall"
+                       % (M2, what, wl["label"].split(":")[0], sec2)), M2, sec2
 
 
-def ref_cuda_rate(wl):
-    """Baseline A of BASELINE.json: the reference's OWN propagateG kernel (unmodified sources recompiled for sm_100a,
-    oracle/_ref/libref_gpu.so, cuRAND Philox states) on the same obstacle map, CUDA-event time of stages 2-5a for
-    30 000 parents x 32 children (its largest launch, KGMT.cu:160-173)."""
+def same_population(wl, plan_mod, local):
+    """Stages 2-4 (sample + integrate + collide + region index) on IDENTICAL inputs: the same parents x 32 children and
+    the same Philox streams through (1) this library (kgmt_stage_propagate), (2) the reference's own propagateG kernel
+    recompiled for sm_100a (baseline A of BASELINE.json; includes its map atomics), (3) the reference's host loop."""
+    out = {"parents": None}
+    try:
+        import cudasbmp_b200 as k
+        from oracle import pyoracle as po
+        cfg, obs = wl["cfg"], wl["obstacles"]
+        parents, what = sample_parents(wl)
+        P = min(len(parents), 30000)
+        parents = parents[:P]
+        M = P * 32
+        out["parents"] = "%d %s x 32 children, Philox key 99" % (P, what)
+        p = k.KGMT(**dict(cfg, N=16, n=8, maxTreeSize=M), device=local, record_candidates=True)
+        p.set_obstacles(obs)
+        best = min(p.stage_propagate(parents, 32, 99, 0) for _ in range(5))
+        out["ours"] = {"value": M / best * 1e3, "unit": UNIT, "ms": best, "what": "kgmt_stage_propagate (stages 2-4, candidate records written)"}
+        valid_ours = float(p.export(plan_mod.ARR_U_VALID)[:M].mean())
+        p.close()
+        if po.ref_gpu() is not None:
+            N, n = 16, 8
+            c1, c2 = N * N, N * N * n * n
+            maps = {kk: np.zeros(c1 if kk.startswith("R1") else c2, dtype=np.int32)
+                    for kk in ("R1", "R2", "R1Valid", "R2Valid", "R1Invalid", "R2Invalid", "R1Avail", "R2Avail")}
+            _, _, gnew, ms = po.ref_gpu_expand(1, 32, parents, np.arange(P, dtype=np.int32), maps, np.ones(c1, np.float32), N, n,
+                                               cfg["width"] / N, cfg["width"] / (N * n), cfg["numDisc"], cfg["agentLength"], obs,
+                                               cfg["width"], cfg["height"], 99, reps=5)
+            out["reference_cuda"] = {"value": M / ms * 1e3, "unit": UNIT, "ms": ms,
+                                     "what": "reference propagateG (KGMT.cu:341-414) unmodified, recompiled for sm_100a, cuRAND Philox"}
+        R = po.ref_host()
+        if R is not None:
+            cores = R.ref_host_hw_threads()
+            pof = (np.arange(M, dtype=np.int32) // 32)
+            sec, _, _, _ = po.ref_host_batch(parents, pof, 99, 0, cfg["numDisc"], cfg["agentLength"], obs, cfg["width"], cfg["height"],
+                                             threads=cores, outputs=False)
+            out["reference_host"] = {"value": M / sec, "unit": UNIT, "cores": cores, "s": sec,
+                                     "what": "reference statePropagator.cu + collisionCheck.cu unmodified, host build"}
+        out["valid_fraction"] = valid_ours
+    except Exception as e:
+        out["error"] = repr(e)
+    return out
+
+
+def reference_plan_ms(runs=11):
+    """The reference's OWN planner end to end on config 1 (its KGMT::plan, XORWOW, recompiled for sm_100a): wall clock
+    around plan() as its 'time inside KGMT' (KGMT.cu:294-295), the constructor's allocations excluded."""
     try:
         from oracle import pyoracle as po
         from cudasbmp_b200 import workloads as w
         if po.ref_gpu() is None:
-            return {"value": None, "unit": UNIT, "kind": "unavailable", "sample": "oracle/_ref/libref_gpu.so missing"}
-        cfg, obs = wl["cfg"], wl["obstacles"]
-        P = 30000
-        parents = w.random_parents(P, obs, seed=7)
-        N, n = 16, 8
-        c1, c2 = N * N, N * N * n * n
-        maps = {k: np.zeros(c1 if k.startswith("R1") else c2, dtype=np.int32)
-                for k in ("R1", "R2", "R1Valid", "R2Valid", "R1Invalid", "R2Invalid", "R1Avail", "R2Avail")}
-        _, _, _, ms = po.ref_gpu_expand(1, 32, parents, np.arange(P, dtype=np.int32), maps, np.ones(c1, np.float32), N, n,
-                                        cfg["width"] / N, cfg["width"] / (N * n), cfg["numDisc"], cfg["agentLength"], obs,
-                                        cfg["width"], cfg["height"], 99, reps=5)
-        return {"value": P * 32 / ms * 1e3, "unit": UNIT, "kind": "reference CUDA kernel propagateG recompiled for sm_100a",
-                "sample": "%d parents x 32 children on the %s map, %.3f ms per launch (best of 5)" % (P, wl["label"].split(":")[0], ms)}
+            return None
+        ms = []
+        for _ in range(runs + 2):
+            r = po.ref_gpu_plan(w.C1, w.C1_INIT, w.C1_GOAL, w.C1_OBSTACLES)
+            ms.append(r["plan_ms"])
+        ms = ms[2:]
+        return {"median_ms": statistics.median(ms), "min_ms": min(ms), "runs": runs,
+                "what": "reference KGMT::plan() on config 1, unmodified sources recompiled for sm_100a, wall clock around plan()"}
     except Exception as e:
-        return {"value": None, "unit": UNIT, "kind": "unavailable", "sample": repr(e)}
+        return {"error": repr(e)}
+
+
+def ttfs_single(k, w, local):
+    """Median time-to-first-solution, 101 seeds, host wall clock from the kgmt_plan call (state allocated, obstacles
+    resident) to the host holding costToGoal != 0."""
+    out = {}
+    for name, cfg, obs, init, goal in (("c1", w.C1, w.C1_OBSTACLES, w.C1_INIT, w.C1_GOAL),
+                                       ("c2", w.C2, w.c2_obstacles(1000), w.C2_INIT, w.C2_GOAL)):
+        p = k.KGMT(**cfg, seed=1, device=local)
+        p.set_obstacles(obs)
+        for s in range(3):
+            p.set_seed(1000 + s); p.plan(init, goal)
+        walls, devs = [], []
+        for s in range(1, 102):
+            p.set_seed(s)
+            tq = time.perf_counter()
+            r = p.plan(init, goal)
+            dtq = time.perf_counter() - tq
+            if r["stop"] == 1:
+                walls.append(dtq * 1e3); devs.append(r["device_ms"])
+        if walls:
+            ws = sorted(walls)
+            out[name] = {"seeds": 101, "solved": len(walls), "median_ms": statistics.median(walls),
+                         "p95_ms": ws[int(0.95 * (len(ws) - 1))], "device_median_ms": statistics.median(devs)}
+        p.close()
+    out["clock"] = "host wall around kgmt_plan"
+    return out
+
+
+def ttfs_multi(k, w, local, rank, world, dist, torch, races=101):
+    """Portfolio race over peer memory: every rank plans the same query with its own seed in ONE launch; the first rank
+    to reach the goal stops the others through a word in their memory (kgmt_peer_race)."""
+    from cudasbmp_b200.sharded import PeerExpander
+    out, race_id = {}, 0
+    for name, cfg, obs, init, goal in (("c1", w.C1, w.C1_OBSTACLES, w.C1_INIT, w.C1_GOAL),
+                                       ("c2", w.C2, w.c2_obstacles(1000), w.C2_INIT, w.C2_GOAL)):
+        p = k.KGMT(**cfg, seed=1, device=local)
+        p.set_obstacles(obs)
+        ex = PeerExpander(p)
+        rows = []
+        for q in range(races + 3):
+            race_id += 1
+            p.set_seed(1000 * q + rank + 1)
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            r = p.peer_race(init, goal, race_id)
+            dt = (time.perf_counter() - t0) * 1e3
+            t = torch.tensor([dt if r["stop"] == 1 else 1e9, dt, float(r["stop"] == 1), r["device_ms"]], dtype=torch.float64, device="cuda")
+            g = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(g, t)
+            g = torch.stack(g).cpu().numpy()
+            if q >= 3:
+                rows.append((g[:, 0].min(), g[:, 1].max(), g[:, 2].sum(), g[:, 3].max()))
+        rows = np.array(rows)
+        solved = rows[rows[:, 0] < 1e8]
+        if len(solved):
+            out[name] = {"races": races, "solved": int(len(solved)), "median_ms": float(np.median(solved[:, 0])),
+                         "p95_ms": float(np.percentile(solved[:, 0], 95)), "all_stopped_median_ms": float(np.median(rows[:, 1])),
+                         "winners_per_race_mean": float(rows[:, 2].mean())}
+        dist.barrier()
+        ex.close(); p.close()
+    out["clock"] = "host wall from a common barrier to the first rank returning a solution (kgmt_peer_race, seed = 1000*race + rank + 1)"
+    return out
+
+
+def bench_c3(k, plan_mod, wl3, local):
+    """Config 3 on one GPU: culled back end (median of 5 plans) and the exhaustive TMA-streamed back end (one plan)."""
+    out = {"workload": wl3["label"]}
+    for name, mode, reps in (("grid", plan_mod.COLLIDE_GRID, 5), ("streamed_exhaustive", plan_mod.COLLIDE_BRUTE, 1)):
+        p = k.KGMT(**wl3["cfg"], seed=1, device=local, collision_mode=mode)
+        p.set_obstacles(wl3["obstacles"])
+        if name == "grid":
+            p.plan(wl3["init"], wl3["goal"])
+        ms, exp = [], 0
+        for s in range(reps):
+            p.set_seed(1 + s)
+            r = p.plan(wl3["init"], wl3["goal"])
+            ms.append(r["device_ms"]); exp += r["expansions"]
+        out[name] = {"plans": reps, "median_ms": statistics.median(ms), "expansions_per_s": exp / (sum(ms) * 1e-3),
+                     "expansions_per_plan": exp / reps, "backend": p.config()["collide_backend"], "tree_size": r["tree_size"], "stop": r["stop"]}
+        p.close()
+    return out
+
+
+def bench_c4(k, w, local, rank, world, dist, torch, Q=1024, reps=5):
+    """Config 4: ONE fixed batch of Q queries on the reference demo map, sharded contiguously over the ranks; every rank
+    plans its shard in one launch (kgmt_plan_batch: a thread-block cluster per query) and the fixed-size result table is
+    all-reduced.  Strong scaling: the same Q at every N.  Reported: queries/s and aggregate expansions/s on the slowest
+    rank's device time and on wall time (barrier to barrier, result gather included), median / p95 time-to-solution of a
+    query (device clock from the start of its rank's launch to the query's last iteration)."""
+    from cudasbmp_b200.multi import shard_range
+    inits, goals = w.random_queries(Q, w.C1_OBSTACLES)
+    seeds = np.arange(Q, dtype=np.uint32)
+    lo, hi = shard_range(Q, rank, world)
+    p = k.KGMT(**w.C1, seed=1, device=local)
+    p.set_obstacles(w.C1_OBSTACLES)
+    cs = p.batch_cluster_size(hi - lo)
+    p.plan_batch(inits[lo:hi], goals[lo:hi], seeds[lo:hi], cluster_size=cs)             # warm-up: allocations, code upload
+    best = None
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        res, ms, _, ws, tts = p.plan_batch(inits[lo:hi], goals[lo:hi], seeds[lo:hi], cluster_size=cs, with_times=True)
+        table = np.zeros((Q, 4), dtype=np.float64)
+        for i, r in enumerate(res):
+            table[lo + i] = (r["stop"], r["expansions"], r["tree_size"], tts[i])
+        t = torch.from_numpy(table).cuda()
+        tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        table = t.cpu().numpy()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        wall, dev_ms = float(tw[0]), float(tm[0])
+        if best is None or wall < best["wall_ms"] * 1e-3:
+            solved = table[:, 0] == 1
+            tt = np.sort(table[solved, 3])
+            best = {"queries": Q, "gpus": world, "cluster_size": cs, "workspaces_per_gpu": ws, "solved": int(solved.sum()),
+                    "device_ms_max": dev_ms, "wall_ms": wall * 1e3, "queries_per_s_device": Q / dev_ms * 1e3,
+                    "queries_per_s_wall": Q / wall, "expansions": float(table[:, 1].sum()),
+                    "expansions_per_s_device": float(table[:, 1].sum()) / dev_ms * 1e3,
+                    "expansions_per_s_wall": float(table[:, 1].sum()) / wall,
+                    "time_to_solution_median_ms": float(np.median(tt)) if len(tt) else None,
+                    "time_to_solution_p95_ms": float(tt[int(0.95 * (len(tt) - 1))]) if len(tt) else None}
+    p.close()
+    return best
+
+
+def bench_c5(k, w, local, rank, world, dist, torch, logs=(20, 22, 24, 26), reps=3, P=32768):
+    """Config 5: ONE iteration of M = 2^log candidates (P parents in free space of the config-2 map, each expanded M/P
+    times), sharded over the ranks with the exchange over peer memory (the library's kernels) and, for comparison, over
+    NCCL; at N = 1 the cooperative kernel and the sharded kernel sequence.  Times: CUDA events, max over ranks."""
+    from cudasbmp_b200.sharded import PeerExpander, ShardedExpander
+    obs = w.c2_obstacles(1000)
+    parents = w.random_parents(P, obs, seed=7)
+    Mmax = 1 << max(logs)
+    p = k.KGMT(**dict(w.C1, maxTreeSize=Mmax + P, numIterations=4), seed=5, device=local, max_candidates=Mmax)
+    p.set_obstacles(obs)
+    out = {"parents": P, "K": 1000, "gpus": world, "points": []}
+
+    def mx(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def one(ex, M, rep):
+        p.set_seed(5 + rep)
+        p.seed_frontier(parents, w.C2_GOAL)
+        p.set_children(M // P)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        return ex.iterate()
+
+    peer = PeerExpander(p, timing=True)
+    for lg in logs:
+        M = 1 << lg
+        pt = {"log2M": lg, "M": M}
+        best = None
+        for rep in range(reps + 1):
+            st = one(peer, M, rep)
+            tot = mx(st["total_ms"])
+            if rep > 0 and (best is None or tot < best):
+                best = tot
+                pt["accepted"] = st["accepted"]
+        pt["peer_total_ms"] = best
+        pt["peer_expansions_per_s"] = M / best * 1e3
+        out["points"].append(pt)
+    peer.close()
+    if dist is not None:
+        dist.barrier()
+    nccl = ShardedExpander(p, timing=True)
+    for pt in out["points"]:
+        M = pt["M"]
+        best = None
+        for rep in range(reps + 1):
+            st = one(nccl, M, rep)
+            comp, comm = mx(st["compute_ms"]), mx(st["comm_ms"])
+            if rep > 0 and (best is None or comp + comm < best[0] + best[1]):
+                best = (comp, comm, st["comm_bytes"])
+        pt["nccl_compute_ms"], pt["nccl_exchange_ms"], pt["nccl_exchange_bytes"] = best
+        pt["nccl_expansions_per_s"] = M / (best[0] + best[1]) * 1e3
+    p.set_stream(None)
+    if world == 1:
+        for pt in out["points"]:
+            M = pt["M"]
+            ms = []
+            for rep in range(reps):
+                p.set_seed(6 + rep)
+                p.seed_frontier(parents, w.C2_GOAL); p.set_children(M // P)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s = torch.cuda.ExternalStream(p.stream)
+                e0.record(s); p.iterate(); e1.record(s); torch.cuda.synchronize()
+                ms.append(e0.elapsed_time(e1))
+            pt["cooperative_kernel_ms"] = min(ms)
+            pt["cooperative_expansions_per_s"] = M / min(ms) * 1e3
+    p.close()
+    return out
+
+
+def fp32_roofline(k, plan_mod, wl, local, rates, value, clock_mhz, sms):
+    """roofline_fp32 of SURVEY.md §8d: exp/s x F_exp(K_tested, S_mean) against the MEASURED lane rate of the instruction
+    class that dominates (compare-class: 4 FSETP per overlap test), with K_tested = K (what the reference executes) and
+    with the pairs the culled kernel really tests (device work counters of a recording plan of the same seed)."""
+    try:
+        p = k.KGMT(**wl["cfg"], seed=21, device=local, record_candidates=True)
+        p.set_obstacles(wl["obstacles"])
+        p.plan(wl["init"], wl["goal"])
+        wc = p.work_counters()
+        p.close()
+        S = wc["steps"] / max(wc["expansions"], 1)
+        pairs = wc["pairs"] / max(wc["steps"], 1)
+        Kobs = len(wl["obstacles"])
+        F_fixed, F_step = 110.0, 60.0                                  # SURVEY.md §8d: F_rng + F_ctrl + tanf ; F_trig + F_dyn per step
+        f_brute = F_fixed + S * (F_step + 4.0 * Kobs)
+        f_culled = F_fixed + S * (F_step + 4.0 * pairs)
+        fsetp = (rates or {}).get("fsetp", {}).get("lane_ops_per_clk_per_sm")
+        ffma = (rates or {}).get("ffma", {}).get("lane_ops_per_clk_per_sm")
+        src = "profiles/issue_rates_b200.json (scripts/native/issue_rate_bench.cu, measured on the box)"
+        if not fsetp:
+            fsetp, src = 64.0, "ASSUMED 64 compare lanes/clk/SM (no measured profiles/issue_rates_b200.json)"
+        peak_cmp = fsetp * sms * clock_mhz * 1e6
+        out = {"steps_per_expansion": S, "pairs_tested_per_step": pairs, "K": Kobs,
+               "lane_ops_per_expansion_brute_equivalent": f_brute, "lane_ops_per_expansion_culled": f_culled,
+               "compare_lane_ops_per_clk_per_sm": fsetp, "ffma_lane_ops_per_clk_per_sm": ffma, "peak_compare_lane_ops_per_s": peak_cmp,
+               "frac_brute_equivalent": value * f_brute / peak_cmp, "frac_culled": value * f_culled / peak_cmp,
+               "peak_source": src, "sm_mhz": clock_mhz,
+               "note": "brute-equivalent > 1 means the culled kernel does less arithmetic than the reference's algorithm needs at this roof"}
+        return out
+    except Exception as e:
+        return {"error": repr(e)}
 
 
 def main():
@@ -162,14 +478,24 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--collide", default="grid", choices=["grid", "brute"])
+    ap.add_argument("--plans-per-step", type=int, default=PLANS_PER_STEP)
+    ap.add_argument("--skip", default="", help="comma list of sections to skip: ttfs,c3,c4,c5,same,fp32,e2e")
+    ap.add_argument("--only-headline", action="store_true", help="headline + e2e only (profiling runs)")
     args = ap.parse_args()
+    skip = set(s for s in args.skip.split(",") if s)
+    if args.only_headline:
+        skip |= {"ttfs", "c3", "c4", "c5", "same", "fp32"}
+        args.no_cpu_baseline = True
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     wl = workload(args.workload)
-    config = {"workload": wl["label"], "step": "one complete plan (all expansion iterations), seed = step index + 1",
+    pps = max(1, args.plans_per_step)
+    config = {"workload": wl["label"],
+              "step": "one batch of %d complete plans (all expansion iterations each), every plan its own seed" % pps,
+              "plans_per_step": pps,
               "sharding": "independent queries/seeds per GPU, no data-path collective", "collision": args.collide,
-              "l2": "flushed between steps (256 MiB device write)"}
+              "l2": "flushed before every plan (256 MiB device write, outside the CUDA-event region)"}
 
     # ------------------------------------------------------------------ reference arm (CPU; rank 0 only)
     if args.impl == "reference":
@@ -197,6 +523,7 @@ def main():
     import torch
     import cudasbmp_b200 as k
     from cudasbmp_b200 import kgmt as K
+    from cudasbmp_b200 import workloads as w
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the product has no CPU path")
     torch.cuda.set_device(local)
@@ -208,13 +535,10 @@ def main():
     mode = K.COLLIDE_GRID if args.collide == "grid" else K.COLLIDE_BRUTE
     plan = k.KGMT(**cfg, seed=1, device=local, collision_mode=mode)
     plan.set_obstacles(wl["obstacles"])
-    L = k.load()
-    import ctypes as C
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    def query(step):
-        plan.set_seed(1 + step * world + rank)          # independent query per step and rank
-        return wl["init"]
+    def seed_of(step, j):
+        return 1 + ((step * pps + j) * world + rank)          # independent query per plan and rank
 
     def barrier():
         torch.cuda.synchronize()
@@ -223,9 +547,15 @@ def main():
         torch.cuda.synchronize()
 
     def run_resident(step):
-        flush.fill_(step & 0xFF)
-        torch.cuda.synchronize()
-        return plan.plan(query(step), wl["goal"])
+        ms, res = 0.0, []
+        for j in range(pps):
+            flush.fill_((step + j) & 0xFF)
+            torch.cuda.synchronize()
+            plan.set_seed(seed_of(step, j))
+            r = plan.plan(wl["init"], wl["goal"])
+            ms += r["device_ms"]
+            res.append(r)
+        return ms, res
 
     for s in range(args.warmup):
         run_resident(s)
@@ -237,61 +567,72 @@ def main():
     t0 = time.perf_counter()
     dev_ms, results = 0.0, []
     for s in range(args.steps):
-        r = run_resident(args.warmup + s)
-        dev_ms += r["device_ms"]
-        results.append(r)
+        ms, res = run_resident(args.warmup + s)
+        dev_ms += ms
+        results += res
     barrier()
     wall = time.perf_counter() - t0
     launches = plan.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
     expansions = sum(r["expansions"] for r in results)
     accepted = sum(r["tree_size"] - 1 for r in results)
 
     # ---- end to end through the C ABI with host buffers
     obs_host = np.ascontiguousarray(wl["obstacles"], dtype=np.float32)
-    for s in range(min(args.warmup, 3)):
-        plan.set_obstacles(obs_host); plan.plan(query(s), wl["goal"])
-    barrier()
-    e2e_exp, d2h = 0, 0
-    t1 = time.perf_counter()
-    for s in range(args.steps):
-        plan.set_obstacles(obs_host)
-        r = plan.plan(query(args.warmup + s), wl["goal"])
-        e2e_exp += r["expansions"]
-        d2h += 128
-        if r["stop"] == 1:
-            path = plan.extract_path()
-            d2h += 128 + 4 + len(path) * 28          # state block + length + the AoS-7 rows
-    barrier()
-    e2e_s = time.perf_counter() - t1
-    cfgd = plan.config()
-    h2d = obs_host.nbytes + cfgd["cull_items"] * 16 + (cfgd["cull_cells"] ** 2 + 4) * 4 + 56 + 128
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- median time-to-first-solution, BASELINE config 1 (reference demo), 101 seeds: host wall clock from the
-    #      kgmt_plan call (state allocated, obstacles resident) to the host holding costToGoal != 0
-    ttfs = None
-    if rank == 0:
-        from cudasbmp_b200 import workloads as w
-        p1 = k.KGMT(**w.C1, seed=1, device=local)
-        p1.set_obstacles(w.C1_OBSTACLES)
+    e2e_exp, d2h, e2e_s = 0, 0, 0.0
+    if "e2e" not in skip:
         for s in range(3):
-            p1.set_seed(1000 + s); p1.plan(w.C1_INIT, w.C1_GOAL)
-        walls, devs, unsolved = [], [], 0
-        for s in range(1, 102):
-            p1.set_seed(s)
-            tq = time.perf_counter()
-            r = p1.plan(w.C1_INIT, w.C1_GOAL)
-            dtq = time.perf_counter() - tq
-            if r["stop"] == 1:
-                walls.append(dtq * 1e3); devs.append(r["device_ms"])
-            else:
-                unsolved += 1
-        if walls:
-            ws = sorted(walls)
-            ttfs = {"config": "config1: reference demo map, init (5,5) goal (2,18), maxTree 30000", "seeds": 101,
-                    "solved": len(walls), "median_ms": statistics.median(walls), "p95_ms": ws[int(0.95 * (len(ws) - 1))],
-                    "device_median_ms": statistics.median(devs), "clock": "host wall around kgmt_plan"}
-        p1.close()
+            plan.set_seed(seed_of(0, s)); plan.set_obstacles(obs_host); plan.plan(wl["init"], wl["goal"])
+        barrier()
+        t1 = time.perf_counter()
+        for s in range(args.steps):
+            for j in range(pps):
+                plan.set_obstacles(obs_host)
+                plan.set_seed(seed_of(args.warmup + s, j))
+                r = plan.plan(wl["init"], wl["goal"])
+                e2e_exp += r["expansions"]
+                d2h += 128
+                if r["stop"] == 1:
+                    path = plan.extract_path()
+                    d2h += 128 + 4 + len(path) * 28          # state block + length + the AoS-7 rows
+        barrier()
+        e2e_s = time.perf_counter() - t1
+    cfgd = plan.config()
+    h2d = pps * (obs_host.nbytes + cfgd["cull_items"] * 16 + (cfgd["cull_cells"] ** 2 + 4) * 4 + 56 + 128)
+
+    # ---- the other named configurations (extra keys of the line)
+    extra = {}
+    t_extra = time.perf_counter()
+    if "ttfs" not in skip:
+        if world == 1:
+            extra["ttfs"] = ttfs_single(k, w, local)
+            extra["ttfs"]["reference_ms"] = reference_plan_ms()
+        else:
+            try:
+                extra["ttfs_multi"] = ttfs_multi(k, w, local, rank, world, dist, torch)
+            except Exception as e:
+                extra["ttfs_multi"] = {"error": repr(e)}
+    if "c3" not in skip and world == 1:
+        try:
+            extra["c3"] = bench_c3(k, K, workload("c3"), local)
+        except Exception as e:
+            extra["c3"] = {"error": repr(e)}
+    if "c4" not in skip:
+        try:
+            extra["c4"] = bench_c4(k, w, local, rank, world, dist, torch)
+            if world > 1:
+                # the same fixed batch on ONE GPU of this box (rank 0 alone), so the line carries its own strong-scaling base
+                one = bench_c4(k, w, local, 0, 1, None, torch) if rank == 0 else None
+                dist.barrier()
+                extra["c4"]["one_gpu_same_box"] = one
+        except Exception as e:
+            extra["c4"] = {"error": repr(e)}
+    if "c5" not in skip:
+        try:
+            extra["c5"] = bench_c5(k, w, local, rank, world, dist, torch)
+        except Exception as e:
+            extra["c5"] = {"error": repr(e)}
+    extra_s = time.perf_counter() - t_extra
 
     # ---- max over ranks, sum of work
     t = torch.tensor([dev_ms, e2e_s, wall], dtype=torch.float64, device="cuda")
@@ -308,19 +649,21 @@ def main():
 
     value = exp_all / (dev_ms_max * 1e-3)
     alpha = acc_all / max(exp_all, 1.0)
-    peaks = {}
+    peaks, rates = {}, {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    try:
+        rates = json.load(open(os.path.join(ROOT, "profiles", "issue_rates_b200.json")))
+    except Exception:
+        pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    # dominant kernel = expand_kernel (one cooperative launch per plan); its duration ~ the plan's device time
-    # minus the reset memsets and the root kernel, measured live below with its own events
-    per_launch_exp = exp_all / world / args.steps
-    kern_ms = dev_ms / args.steps
+    n_plans = args.steps * pps
+    per_launch_exp = exp_all / world / n_plans                 # dominant kernel: ONE cooperative launch per plan
+    kern_ms = dev_ms / n_plans
     achieved = per_launch_exp * (B_EXP + B_INS * alpha) / (kern_ms * 1e-3) / 1e9
     solved = [r for r in results if r["stop"] == 1]
-    # ncu-derived per-launch figures of the dominant kernel (DRAM bytes, warp instructions per expansion)
     prof = {}
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_inputs.json")))
@@ -328,40 +671,52 @@ def main():
             prof = {}
     except Exception:
         prof = {}
-    sm_clock_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+    sm_mhz = float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+    sm_clock_hz = 1e6 * sm_mhz
     issue_peak = cfgd["sms"] * 4 * sm_clock_hz                 # one warp instruction per scheduler per clock
     ipe = prof.get("warp_instructions_per_expansion")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": config,
-        "e2e": {"value": e2e_all / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h / max(args.steps, 1)),
-                "ms_per_step": 1e3 * e2e_s_max / args.steps},
+        "e2e": {"value": (e2e_all / e2e_s_max) if e2e_s_max > 0 else None, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h / max(args.steps, 1)), "ms_per_step": 1e3 * e2e_s_max / args.steps},
         "gpu_launches": int(launches_all),
         "clocks": clocks,
+        "timed_region_s": dev_ms_max * 1e-3, "timed_wall_s": wall_max,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": prof.get("dram_bytes_per_launch"), "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-                     "kernel": "kgmt::expand_kernel<grid|brute, LOOP> (cooperative, one launch per plan)",
+                     "kernel": "kgmt::expand_kernel<grid|brute, RECORD, chunks in flight> (cooperative, one launch per plan)",
                      "algorithmic_bytes_per_expansion": B_EXP + B_INS * alpha, "accept_ratio": alpha,
                      "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, %s)" % prof.get("source"),
                      "algorithmic_bytes_per_launch": per_launch_exp * (B_EXP + B_INS * alpha),
-                     "note": "stages 2-4 are FP32-issue bound, not HBM bound (DESIGN.md); see roofline_issue and profiles/"},
+                     "launch_ms": kern_ms,
+                     "note": "stages 2-4 are instruction-issue bound, not HBM bound (DESIGN.md); see roofline_issue, roofline_fp32 and profiles/"},
         "roofline_issue": {"bound": "warp-instruction issue", "unit": "G warp-inst/s",
                            "achieved": (per_launch_exp * ipe / (kern_ms * 1e-3) / 1e9) if ipe else None,
                            "peak": issue_peak / 1e9, "frac": (per_launch_exp * ipe / (kern_ms * 1e-3) / issue_peak) if ipe else None,
                            "warp_instructions_per_expansion": ipe, "avg_active_lanes": prof.get("avg_active_lanes"),
-                           "peak_source": "SMs x 4 schedulers x SM clock under load (nvidia-smi during the timed region)",
+                           "peak_source": "SMs x 4 schedulers x SM clock under load (nvidia-smi during the timed region); "
+                                          "1 warp-inst/clk/scheduler confirmed by profiles/issue_rates_b200.json" if rates else
+                                          "SMs x 4 schedulers x SM clock under load (nvidia-smi during the timed region)",
                            "source": prof.get("source")},
-        "plan": {"expansions_per_plan": exp_all / world / args.steps, "tree_size_mean": acc_all / world / args.steps + 1,
+        "plan": {"expansions_per_plan": per_launch_exp, "tree_size_mean": acc_all / world / n_plans + 1,
                  "iterations_mean": statistics.mean(r["iterations"] for r in results),
-                 "solved": len(solved), "stops": sorted(set(r["stop"] for r in results)),
+                 "plans_timed": n_plans, "solved": len(solved), "stops": sorted(set(r["stop"] for r in results)),
+                 "device_ms_per_plan": kern_ms,
                  "time_to_first_solution_ms_median": statistics.median(r["device_ms"] for r in solved) if solved else None,
-                 "host_wall_ms_per_plan": 1e3 * wall_max / args.steps},
+                 "host_wall_ms_per_plan": 1e3 * wall_max / n_plans},
         "collide_backend": cfgd,
+        "extra_sections_s": extra_s,
     }
-    line["ttfs"] = ttfs
-    if not args.no_cpu_baseline:
-        line["ref_cuda_baseline"] = ref_cuda_rate(wl)
+    line.update(extra)
+    if "fp32" not in skip:
+        line["roofline_fp32"] = fp32_roofline(k, K, wl, local, rates, value / world, sm_mhz, cfgd["sms"])
+    if "same" not in skip and world == 1:
+        line["same_population"] = same_population(wl, K, local)
+        sp = line["same_population"]
+        if "reference_cuda" in sp:
+            line["ref_cuda_baseline"] = dict(sp["reference_cuda"], kind="reference CUDA kernel propagateG recompiled for sm_100a", sample=sp["parents"])
     if not args.no_cpu_baseline:
         try:
             base, _, _ = cpu_reference_rate(wl, seconds=12.0)

@@ -66,9 +66,7 @@ struct kgmt_ctx {
     float4* dParents = nullptr; size_t parentsCap = 0;
     /* launch configuration */
     int col = COL_GRID_SMEM; size_t smemBytes = 0; int useHist = 0;
-    size_t smemLoop = 0;               /* smemBytes + the parked-edge slots of the cooperative kernel */
     int gridLoop = 0, gridMax = 0;
-    int group = 1;                     /* chunks in flight per warp (expand_group); 1 = one chunk at a time */
     bool configured = false;
     int cfgCol = -1; size_t cfgSmem = 0;      /* what the launch configuration was resolved for */
     bool begun = false;
@@ -120,9 +118,6 @@ static int fail(kgmt_ctx* c, int code, const char* fmt, ...) {
     } while (0)
 
 #define KGMT_ITERLOG_BYTES (256 * 64)
-#ifndef KGMT_DEFAULT_GROUP
-#define KGMT_DEFAULT_GROUP 1         /* chunks in flight per warp in phase A (1 = no lane refill) */
-#endif
 static const size_t MAX_DYN_SMEM = 227u * 1024u - 8u * 1024u;   /* leave room for static shared + reserve */
 
 /* -------------------------------------------------------------------------------- kernels table */
@@ -130,19 +125,7 @@ typedef void (*expand_fn)(const KArgs, int);
 template <int COL> static expand_fn pick_expand(bool rec) {
     return rec ? (expand_fn)expand_kernel<COL, true> : (expand_fn)expand_kernel<COL, false>;
 }
-template <int G> static expand_fn pick_group(bool rec) {
-    return rec ? (expand_fn)expand_kernel<COL_GRID_SMEM, true, G> : (expand_fn)expand_kernel<COL_GRID_SMEM, false, G>;
-}
-/* group = chunks a warp keeps in flight per pass of phase A (lane refill); only the shared-memory grid back end has it */
-static expand_fn expand_entry(int col, bool rec, int group = 1) {
-    if (col == COL_GRID_SMEM) {
-        switch (group) {
-            case 2: return pick_group<2>(rec);
-            case 3: return pick_group<3>(rec);
-            case 4: return pick_group<4>(rec);
-            default: break;
-        }
-    }
+static expand_fn expand_entry(int col, bool rec) {
     switch (col) {
         case COL_GRID_SMEM: return pick_expand<COL_GRID_SMEM>(rec);
         case COL_GRID_GLOBAL: return pick_expand<COL_GRID_GLOBAL>(rec);
@@ -219,26 +202,17 @@ static int configure(kgmt_ctx* ctx) {
     }
     if (col == COL_GRID_GLOBAL || col == COL_BRUTE_GLOBAL) colBytes = 0;
     ctx->col = col;
-    /* chunks in flight per warp: params.reserved[2], else the environment variable KGMT_GROUP (experiments), else the
-     * default; every extra chunk parks 32 edges of 32 B per warp in shared memory behind the collision data */
-    {
-        int g = ctx->p.reserved[2];
-        if (g <= 0) { const char* e = getenv("KGMT_GROUP"); g = e ? atoi(e) : KGMT_DEFAULT_GROUP; }
-        ctx->group = (col == COL_GRID_SMEM) ? std::max(1, std::min(g, 4)) : 1;
-    }
-    const size_t slotBytes = (size_t)WARPS * (ctx->group - 1) * 32 * sizeof(EdgeSlot);
     ctx->smemBytes = histBytes + colBytes;
-    ctx->smemLoop = ctx->smemBytes + slotBytes;
     /* a new obstacle set of the same size class resolves to the same kernels and shared-memory size: keep the launch
      * configuration (the attribute / occupancy queries below are ~100 us of driver calls per kgmt_set_obstacles) */
-    if (ctx->configured && ctx->cfgCol == col && ctx->cfgSmem == ctx->smemLoop) return KGMT_OK;
-    ctx->cfgCol = col; ctx->cfgSmem = ctx->smemLoop;
+    if (ctx->configured && ctx->cfgCol == col && ctx->cfgSmem == ctx->smemBytes) return KGMT_OK;
+    ctx->cfgCol = col; ctx->cfgSmem = ctx->smemBytes;
     int occ = 1 << 30;
     for (int rec = 0; rec < 2; ++rec) {
-        expand_fn f = expand_entry(col, rec != 0, ctx->group);
-        CU(cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemLoop));
+        expand_fn f = expand_entry(col, rec != 0);
+        CU(cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemBytes));
         int o = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void*)f, TILE, ctx->smemLoop));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void*)f, TILE, ctx->smemBytes));
         occ = std::min(occ, o);
     }
     CU(cudaFuncSetAttribute((const void*)propagate_entry(col), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)colBytes));
@@ -704,9 +678,9 @@ int kgmt_begin(kgmt_ctx* ctx, const float* initial7, const float* goal7) {
 
 static int launch_expand(kgmt_ctx* ctx, int maxIters) {
     KArgs A = make_args(ctx);
-    expand_fn f = expand_entry(ctx->col, ctx->p.record_candidates != 0, ctx->group);
+    expand_fn f = expand_entry(ctx->col, ctx->p.record_candidates != 0);
     void* args[] = {(void*)&A, (void*)&maxIters};
-    CU(cudaLaunchCooperativeKernel((const void*)f, dim3(ctx->gridLoop), dim3(TILE), args, ctx->smemLoop, ctx->stream));
+    CU(cudaLaunchCooperativeKernel((const void*)f, dim3(ctx->gridLoop), dim3(TILE), args, ctx->smemBytes, ctx->stream));
     ctx->launches += 1;
     ctx->planLaunches += 1;
     return KGMT_OK;
@@ -1621,7 +1595,7 @@ int kgmt_iteration_log(kgmt_ctx* ctx, int enable, unsigned long long* out8, int 
 int kgmt_get_config(const kgmt_ctx* ctx, int* out8) {
     if (!ctx || !out8) return KGMT_ERR_INVALID;
     out8[0] = ctx->col; out8[1] = ctx->cullC; out8[2] = ctx->numItems; out8[3] = (int)ctx->smemBytes;
-    out8[4] = ctx->gridLoop; out8[5] = ctx->numSMs; out8[6] = ctx->useHist | (ctx->group << 8); out8[7] = ctx->K;
+    out8[4] = ctx->gridLoop; out8[5] = ctx->numSMs; out8[6] = ctx->useHist; out8[7] = ctx->K;
     return KGMT_OK;
 }
 

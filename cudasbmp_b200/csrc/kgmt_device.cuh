@@ -201,39 +201,6 @@ __device__ __forceinline__ bool propagate_edge(float4& s, const Controls& u, con
     return valid;
 }
 
-/* The same edge as a RESUMABLE object: begin() + one step() per call.  Phase A keeps several chunks of candidates in
- * flight per warp and hands a lane whose edge has ended (collision, workspace bounds, or all steps done) the next
- * pending edge, so the lanes freed by early exits do not idle until the slowest edge of the chunk is done.
- * step() is the loop body of propagate_edge, operation for operation (same intrinsics, same order): the results are
- * bit-identical whichever lane runs the edge (tests: every plan == its chunks_in_flight = 1 twin). */
-template <class Collide>
-struct EdgeRun {
-    float x, y, th, v, a, dt, tanS;
-    typename Collide::Cursor cur;
-    int i;
-    __device__ __forceinline__ void begin(const float4 s, float a_, float dt_, float tanS_, const Collide& col) {
-        x = s.x; y = s.y; th = s.z; v = s.w; a = a_; dt = dt_; tanS = tanS_; i = 0;
-        cur = col.start(x, y);
-    }
-    /* 0: the edge goes on; 1: ended valid (all numDisc steps); 2: ended invalid (statePropagator.cu:42-45 or :61-64) */
-    __device__ __forceinline__ int step(const DynParams& p, const Collide& col) {
-        const float px = x, py = y;
-        float sn, cs;
-        sincosf(th, &sn, &cs);
-        x = __fmaf_rn(dt, __fmul_rn(v, cs), x);
-        y = __fmaf_rn(dt, __fmul_rn(v, sn), y);
-        if (x <= 0.0f || x >= p.W || y <= 0.0f || y >= p.H) return 2;
-        const float vl = (p.L == 1.0f) ? v : __fdiv_rn(v, p.L);
-        th = __fmaf_rn(dt, __fmul_rn(vl, tanS), th);
-        v = __fmaf_rn(a, dt, v);
-        const float bnx = (px > x) ? x : px, bxx = (px > x) ? px : x;
-        const float bny = (py > y) ? y : py, bxy = (py > y) ? py : y;
-        if (col.hit(cur, x, y, bnx, bny, bxx, bxy)) return 2;
-        ++i;
-        return i >= p.numDisc ? 1 : 0;
-    }
-};
-
 /* ---------------------------------------------------------- tile-streamed exhaustive test --
  * The same edge (propagateAndCheck, statePropagator.cu:21-75) when the obstacle set does not fit shared memory in
  * one piece: the obstacles stream through shared memory in tiles and the edge is re-integrated once per tile (the

@@ -442,87 +442,6 @@ __device__ __forceinline__ void expand_chunk(const KArgs& A, const IterView& it,
     chunk_finish<RECORD, SHARD>(A, it, cc, c, lane, hV, hI, scoresOk);
 }
 
-/* ------------------------------------------- phase A: G chunks in flight per warp, lanes refilled ----
- * ~40 % of config 2's edges end early (collision / bounds), so with one candidate per lane for a whole chunk the
- * integration loop runs at ~21 of 32 lanes (profiles/r01j_*).  Here a warp takes up to G consecutive chunks:
- *   prologue   stage 2 + parent reads for all G chunks at full width (chunk_setup); the edges of chunks 1..G-1 are
- *              parked in this warp's shared-memory slots (state, a, dt, tan(steering): 32 B each)
- *   run loop   lane l starts on candidate l of chunk 0; a lane whose edge ends writes the exit state into the edge's
- *              slot (its own registers for chunk 0) and takes the next parked edge (ballot + popcount hand-out, in
- *              slot order); the loop ends when no edge is parked or running
- *   epilogue   stage 5a for the G chunks at full width (chunk_finish), each lane for the candidates it set up
- * Who runs an edge does not change its arithmetic (EdgeRun), and chunk_finish sees the same (state, valid) per
- * candidate in the same chunk order, so trees, maps and ballots are bit-identical to G = 1. */
-struct EdgeSlot { float4 s; float4 c; };      /* parked: state | (a, dt, tanS, live);  done: exit state | (valid, ...) */
-
-template <class Collide, bool RECORD, int G>
-__device__ __forceinline__ void expand_group(const KArgs& A, const IterView& it, const DynParams& dyn, const Collide& col,
-                                             int c0, int nch, int lane, int* hV, int* hI, bool& scoresOk, EdgeSlot* slots) {
-    ChunkCand cc[G];
-    float dts[G], tans[G];
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        cc[g] = ChunkCand{};
-        if (g < nch) cc[g] = chunk_setup(A, it, c0 + g, lane);
-        dts[g] = __fdiv_rn(cc[g].u.duration, (float)dyn.numDisc);
-        tans[g] = tanf(cc[g].u.steering);
-        if (g >= 1 && g < nch)
-            slots[(g - 1) * 32 + lane] = EdgeSlot{cc[g].x, make_float4(cc[g].u.a, dts[g], tans[g], cc[g].live ? 1.0f : 0.0f)};
-    }
-    __syncwarp();
-    EdgeRun<Collide> run;
-    run.begin(cc[0].x, cc[0].u.a, dts[0], tans[0], col);
-    bool running = cc[0].live;
-    int tag = -1;                                   /* -1: this lane's own chunk-0 candidate, else the slot it runs */
-    int next = 0;
-    const int end = (nch - 1) * 32;
-    bool val0 = false;
-    unsigned steps = 0u, pairs = 0u;
-    const unsigned below = (1u << lane) - 1u;
-    for (;;) {
-        const unsigned idle = __ballot_sync(0xffffffffu, !running);
-        if (idle != 0u && next < end) {
-            const int e = next + __popc(idle & below);
-            if (!running && e < end) {
-                const EdgeSlot sl = slots[e];
-                if (sl.c.w != 0.0f) { run.begin(sl.s, sl.c.x, sl.c.y, sl.c.z, col); running = true; tag = e; }
-            }
-            next = min(next + __popc(idle), end);
-        }
-        if (!__any_sync(0xffffffffu, running)) { if (next >= end) break; continue; }
-        if (running) {
-            const int r = run.step(dyn, col);
-            if (RECORD) steps += 1u;
-            if (r != 0) {
-                running = false;
-                if (RECORD) pairs += run.cur.pairs;
-                const float4 out = make_float4(run.x, run.y, run.th, run.v);
-                if (tag < 0) { cc[0].x = out; val0 = (r == 1); }
-                else { slots[tag].s = out; slots[tag].c.x = (r == 1) ? 1.0f : 0.0f; }
-            }
-        }
-    }
-    __syncwarp();
-    if (RECORD) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { steps += __shfl_xor_sync(0xffffffffu, steps, o); pairs += __shfl_xor_sync(0xffffffffu, pairs, o); }
-        if (lane == 0) { atomicAdd(&A.st->stepsDone, (unsigned long long)steps); atomicAdd(&A.st->pairsTested, (unsigned long long)pairs); }
-    }
-    cc[0].valid = val0;
-    chunk_finish<RECORD, false>(A, it, cc[0], c0, lane, hV, hI, scoresOk);
-#pragma unroll
-    for (int g = 1; g < G; ++g) {
-        if (g < nch) {
-            if (cc[g].live) {
-                const EdgeSlot sl = slots[(g - 1) * 32 + lane];
-                cc[g].x = sl.s; cc[g].valid = sl.c.x != 0.0f;
-            }
-            chunk_finish<RECORD, false>(A, it, cc[g], c0 + g, lane, hV, hI, scoresOk);
-        }
-    }
-    __syncwarp();                                   /* the slots may be re-used by the next group */
-}
-
 /* ------------------------------------------- phase A with the obstacles STREAMED in tiles ----
  * Exhaustive test when the obstacle set exceeds the shared-memory staging budget (BASELINE config 3).  The obstacle
  * array cycles through two 16 KB shared-memory tiles filled by the TMA engine (cp.async.bulk + mbarrier); the CTA takes
@@ -658,7 +577,6 @@ struct ColSet {
     CollideSmemAll allS, allG;
     int* hV; int* hI;                       /* per-CTA R1 histograms (shared memory) */
     TileStream stream;                      /* COL_BRUTE_STREAM only */
-    EdgeSlot* slots;                        /* COL_GRID_SMEM with chunks in flight > 1: [WARPS][(G-1)*32] parked edges */
 };
 
 /* carve dynamic shared memory [R1 histograms][collision data] and stage the collision structure into it with
@@ -668,7 +586,6 @@ __device__ __forceinline__ ColSet stage_collision(const KArgs& A, unsigned char*
     const int tid = threadIdx.x;
     ColSet cs;
     cs.stream = TileStream{};
-    cs.slots = nullptr;
     cs.hV = reinterpret_cast<int*>(smem_raw);
     cs.hI = cs.hV + (A.useHist ? A.c1 : 0);
     unsigned char* colBase = smem_raw + (A.useHist ? ((2 * A.c1 * 4 + 15) & ~15) : 0);
@@ -692,7 +609,6 @@ __device__ __forceinline__ ColSet stage_collision(const KArgs& A, unsigned char*
         if (COL == COL_GRID_SMEM) {
             sCellStart = reinterpret_cast<const int*>(colBase);
             sItems = reinterpret_cast<const float4*>(colBase + bytes0);
-            cs.slots = reinterpret_cast<EdgeSlot*>(colBase + bytes0 + bytes1);       /* both multiples of 16 */
         } else {
             sObs = reinterpret_cast<const float4*>(colBase);
         }
@@ -721,7 +637,7 @@ __device__ __forceinline__ void stream_drain(const TileStream& ts) {
     mbar_wait(&ts.full[(ts.g + 1u) & 1u], ((ts.g + 1u) >> 1) & 1u);
 }
 
-template <int COL, bool RECORD, class Group, int G = 1>
+template <int COL, bool RECORD, class Group>
 __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
     __shared__ int sRed[WARPS];
     __shared__ float sP[1024];
@@ -783,24 +699,6 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
             int t = 0;
             /* parents were inserted by the previous phase B, possibly still running on other CTAs */
             if (c < it.numChunks) wait_ge(&st->insertDone, S.blocksTotal);
-            if (COL == COL_GRID_SMEM && G > 1) {
-                /* groups of up to G consecutive chunks per warp with lane refill (expand_group).  Group sizes shrink as
-                 * the iteration drains (guided self-scheduling) so the tail stays one chunk long; the first group is
-                 * taken by position, the ticket (which starts at totalWarps) is read relative to it. */
-                EdgeSlot* mySlots = cs.slots + warp * ((G - 1) * 32);
-                const int g0 = max(1, min(G, it.numChunks / totalWarps));
-                const int off = totalWarps * (g0 - 1);
-                int g = g0;
-                c = gw * g0;
-                while (c < it.numChunks) {
-                    const int nch = min(g, it.numChunks - c);
-                    const int gn = max(1, min(G, (it.numChunks - (c + nch)) / totalWarps));      /* size of the next group */
-                    if (lane == 0) t = (int)atomicAdd(ticket, (unsigned)gn);
-                    expand_group<CollideGrid, RECORD, G>(A, it, dyn, colGridS, c, nch, lane, hV, hI, scoresOk, mySlots);
-                    c = __shfl_sync(0xffffffffu, t, 0) + off;
-                    g = gn;
-                }
-            } else
             while (c < it.numChunks) {
                 if (lane == 0) t = (int)atomicAdd(ticket, 1u);
                 if (COL == COL_GRID_SMEM)        expand_chunk<CollideGrid, RECORD>(A, it, dyn, colGridS, c, lane, hV, hI, scoresOk);
@@ -894,13 +792,13 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
 #else
 #define KGMT_EXPAND_BOUNDS __launch_bounds__(TILE, KGMT_EXPAND_MIN_CTAS)
 #endif
-template <int COL, bool RECORD, int G = 1>
+template <int COL, bool RECORD>
 __global__ void KGMT_EXPAND_BOUNDS expand_kernel(const KArgs A, int maxIters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t sBar;
     GridGroup grp;
     ColSet cs = stage_collision<COL>(A, smem_raw, &sBar);
-    run_plan<COL, RECORD, GridGroup, G>(A, maxIters, grp, cs);
+    run_plan<COL, RECORD, GridGroup>(A, maxIters, grp, cs);
     if (COL == COL_BRUTE_STREAM) stream_drain(cs.stream);
 }
 

@@ -189,7 +189,7 @@ class KGMT:
     def __init__(self, width=20.0, height=20.0, N=16, n=8, numIterations=100, maxTreeSize=30000, numDisc=10,
                  agentLength=1.0, goalThreshold=0.5, *, seed=1, device=-1, max_candidates=0,
                  collision_mode=COLLIDE_GRID, record_candidates=False, cull_cells=0, stage_limit_bytes=0,
-                 ctas_per_sm=0, chunks_in_flight=0, car=None, car_yaml=None):
+                 ctas_per_sm=0, car=None, car_yaml=None):
         L = load()
         p = default_params()
         p.width, p.height, p.N, p.n = width, height, N, n
@@ -199,7 +199,6 @@ class KGMT:
         p.collision_mode, p.record_candidates, p.cull_cells = collision_mode, int(bool(record_candidates)), cull_cells
         p.reserved[0] = stage_limit_bytes
         p.reserved[1] = ctas_per_sm          # 0 = as many as fit
-        p.reserved[2] = chunks_in_flight     # 32-candidate chunks a warp keeps in flight per pass of phase A (0 = default)
         if car_yaml is not None:             # systems/car.yaml-style model file (flat key: value; empty = defaults)
             bad = C.c_int(0)
             if L.kgmt_params_from_yaml(os.fsencode(car_yaml), C.byref(p), C.byref(bad)) != OK:

@@ -70,8 +70,7 @@ typedef struct kgmt_params {
     int      cull_cells;             /* cull grid is cull_cells x cull_cells; 0 = choose from the obstacle set */
     int      reserved[5];            /* [0]: shared-memory staging budget for the collision data in bytes (0 = 60 KB);
                                         [1]: resident CTAs per SM of the persistent kernel (0 = all that fit);
-                                        [2]: candidates a warp keeps in flight per pass of phase A, in chunks of 32
-                                             (0 = default); rest 0 */
+                                        rest 0 */
     /* The car model ("systems/car.yaml" of the reference is an empty file; its dynamics and control ranges are literals
      * in statePropagator.cu:17-19).  Control c is drawn as lo + u * (hi - lo), u = curand_uniform in (0, 1]:
      *   a        = fmaf(u0, (float)(accel_max - accel_min), (float)accel_min)              :17  u0 * 10.0f - 5.0f
