@@ -211,7 +211,7 @@ def same_population(wl, plan_mod, local):
     return out
 
 
-def reference_plan_ms(runs=11):
+def reference_plan_ms(runs=7):
     """The reference's OWN planner end to end on config 1 (its KGMT::plan, XORWOW, recompiled for sm_100a): wall clock
     around plan() as its 'time inside KGMT' (KGMT.cu:294-295), the constructor's allocations excluded."""
     try:
@@ -219,13 +219,16 @@ def reference_plan_ms(runs=11):
         from cudasbmp_b200 import workloads as w
         if po.ref_gpu() is None:
             return None
-        ms = []
-        for _ in range(runs + 2):
+        ms, wall = [], []
+        for i in range(runs + 2):
             r = po.ref_gpu_plan(w.C1, w.C1_INIT, w.C1_GOAL, w.C1_OBSTACLES)
-            ms.append(r["plan_ms"])
-        ms = ms[2:]
+            if i >= 2:
+                ms.append(r["inside_ms"]); wall.append(r["plan_wall_ms"])
+            time.sleep(1.01)                                     # the reference seeds cuRAND from time(NULL): one seed per second
         return {"median_ms": statistics.median(ms), "min_ms": min(ms), "runs": runs,
-                "what": "reference KGMT::plan() on config 1, unmodified sources recompiled for sm_100a, wall clock around plan()"}
+                "plan_wall_incl_csv_median_ms": statistics.median(wall),
+                "what": "reference KGMT::plan() on config 1, unmodified sources recompiled for sm_100a: its own 'time inside KGMT' "
+                        "(std::clock around its loop, KGMT.cu:82,294-295), seeds = time(NULL)"}
     except Exception as e:
         return {"error": repr(e)}
 
@@ -333,10 +336,10 @@ def bench_c4(k, w, local, rank, world, dist, torch, Q=1024, reps=5):
         if dist is not None:
             dist.barrier()
         t0 = time.perf_counter()
-        res, ms, _, ws, tts = p.plan_batch(inits[lo:hi], goals[lo:hi], seeds[lo:hi], cluster_size=cs, with_times=True)
+        res, ms, _, ws = p.plan_batch(inits[lo:hi], goals[lo:hi], seeds[lo:hi], cluster_size=cs)
         table = np.zeros((Q, 4), dtype=np.float64)
         for i, r in enumerate(res):
-            table[lo + i] = (r["stop"], r["expansions"], r["tree_size"], tts[i])
+            table[lo + i] = (r["stop"], r["expansions"], r["tree_size"], r["done_ms"])
         t = torch.from_numpy(table).cuda()
         tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
         if dist is not None:

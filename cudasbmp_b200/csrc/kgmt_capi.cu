@@ -58,8 +58,8 @@ struct kgmt_ctx {
     int* dCellStart = nullptr; float4* dCellItems = nullptr; size_t cellStartCap = 0, cellItemsCap = 0;
     int cullC = 1, cellStartInts = 4, numItems = 0;
     float cullInvX = 0.f, cullInvY = 0.f;
-    std::vector<float> hObs;
-    std::vector<int> hStart; std::vector<float> hItems, hObsPadded;   /* staging of the asynchronous uploads */
+    float* hObsPinned = nullptr; size_t hObsPinnedCap = 0;            /* pinned staging of kgmt_set_obstacles_host */
+    int* hCullTotal = nullptr; int* dCullTotal = nullptr;             /* item count of the cull grid: pinned host word, device word */
     std::vector<unsigned char> hPath;  /* staging of kgmt_extract_path */
     /* staging */
     void* scratch = nullptr; size_t scratchBytes = 0;
@@ -79,6 +79,7 @@ struct kgmt_ctx {
         int numWs = 0, clusterSize = 0, Qcap = 0, maxPath = 0;
         float4 *treeState = nullptr, *treeCtrl = nullptr, *stageState = nullptr, *stageCtrl = nullptr;
         int *treeParent = nullptr, *mapSlab = nullptr, *blockSum = nullptr, *queryTicket = nullptr, *wsQuery = nullptr, *pathLen = nullptr;
+        unsigned long long* launchT0 = nullptr;
         unsigned *chunkMask = nullptr, *ticket = nullptr;
         float4 *initState = nullptr, *initCtrl = nullptr; float2* goalXY = nullptr; uint32_t* seeds = nullptr;
         DevState* states = nullptr; float* paths = nullptr;
@@ -242,87 +243,69 @@ static int configure(kgmt_ctx* ctx) {
     return KGMT_OK;
 }
 
-/* uniform grid over the workspace: CSR of obstacle AABBs per cell (host build) */
-static int cull_cell(float v, float inv, int C) {
-    const float t = std::floor(v * inv);
-    if (!(t > 0.0f)) return 0;
-    if (t >= (float)C) return C - 1;
-    return (int)t;
-}
+/* uniform grid over the workspace: CSR of obstacle AABBs per cell, built ON THE DEVICE from ctx->dObs (cull_* kernels);
+ * the host learns one number, the item count, which sizes the shared-memory staging of the planner kernels */
 static int build_cull_grid(kgmt_ctx* ctx) {
     const int K = ctx->K;
     int C = ctx->p.cull_cells;
     if (C <= 0) C = (int)std::ceil(1.5 * std::sqrt((double)std::max(K, 1)));   /* measured on config 2: 32 -> 48 cells per side = -2.8 % plan time */
     C = std::max(1, std::min(C, 512));
     const float invX = (float)C / ctx->p.width, invY = (float)C / ctx->p.height;
-    std::vector<int>& start = ctx->hStart;
-    start.assign((size_t)C * C + 1, 0);
-    const float* o = ctx->hObs.data();
-    for (int k = 0; k < K; ++k) {
-        const int x0 = cull_cell(o[4 * k], invX, C), x1 = cull_cell(o[4 * k + 2], invX, C);
-        const int y0 = cull_cell(o[4 * k + 1], invY, C), y1 = cull_cell(o[4 * k + 3], invY, C);
-        for (int y = y0; y <= y1; ++y)
-            for (int x = x0; x <= x1; ++x) start[(size_t)y * C + x + 1] += 1;
-    }
-    for (size_t i = 0; i < (size_t)C * C; ++i) start[i + 1] += start[i];
-    const int realItems = start[(size_t)C * C];
-    const int numItems = realItems + 3;          /* + three boxes nothing overlaps: the cell walk reads four entries per trip */
-    std::vector<float>& items = ctx->hItems;
-    items.assign((size_t)numItems * 4, 0.0f);
-    for (int k = realItems; k < numItems; ++k) {
-        items[(size_t)k * 4] = INFINITY; items[(size_t)k * 4 + 1] = INFINITY;
-        items[(size_t)k * 4 + 2] = -INFINITY; items[(size_t)k * 4 + 3] = -INFINITY;
-    }
-    std::vector<int> fill(start.begin(), start.end() - 1);
-    for (int k = 0; k < K; ++k) {
-        const int x0 = cull_cell(o[4 * k], invX, C), x1 = cull_cell(o[4 * k + 2], invX, C);
-        const int y0 = cull_cell(o[4 * k + 1], invY, C), y1 = cull_cell(o[4 * k + 3], invY, C);
-        for (int y = y0; y <= y1; ++y)
-            for (int x = x0; x <= x1; ++x) {
-                const int at = fill[(size_t)y * C + x]++;
-                memcpy(&items[(size_t)at * 4], &o[4 * k], 16);
-            }
-    }
-    const int startInts = (int)((start.size() + 3) & ~(size_t)3);
-    start.resize(startInts, realItems);
+    const int cells = C * C;
+    const int startInts = (cells + 1 + 3) & ~3;
+    cudaStream_t s = ctx->stream;
     if ((size_t)startInts > ctx->cellStartCap) {
         if (ctx->dCellStart) cudaFree(ctx->dCellStart);
+        ctx->dCellStart = nullptr; ctx->cellStartCap = 0;
         CU(cudaMalloc(&ctx->dCellStart, (size_t)startInts * 4));
         ctx->cellStartCap = startInts;
     }
-    if ((size_t)std::max(numItems, 1) > ctx->cellItemsCap) {
+    if (!ctx->hCullTotal) CU(cudaHostAlloc(&ctx->hCullTotal, 16, cudaHostAllocDefault));
+    if (!ctx->dCullTotal) CU(cudaMalloc(&ctx->dCullTotal, 16));
+    CU(cudaMemsetAsync(ctx->dCellStart, 0, (size_t)startInts * 4, s));
+    cull_count_kernel<<<(cells + 127) / 128, 128, 0, s>>>(ctx->dObs, K, C, invX, invY, ctx->dCellStart);
+    cull_scan_kernel<<<1, 1024, 0, s>>>(ctx->dCellStart, cells, startInts, ctx->dCullTotal);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ctx->hCullTotal, ctx->dCullTotal, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const int realItems = *ctx->hCullTotal;
+    const int numItems = realItems + 3;          /* + three boxes nothing overlaps: the cell walk reads four entries per trip */
+    if ((size_t)numItems > ctx->cellItemsCap) {
         if (ctx->dCellItems) cudaFree(ctx->dCellItems);
-        CU(cudaMalloc(&ctx->dCellItems, (size_t)std::max(numItems, 1) * 16));
-        ctx->cellItemsCap = std::max(numItems, 1);
+        ctx->dCellItems = nullptr; ctx->cellItemsCap = 0;
+        const size_t cap = (size_t)numItems + (size_t)numItems / 4 + 64;
+        CU(cudaMalloc(&ctx->dCellItems, cap * 16));
+        ctx->cellItemsCap = cap;
     }
-    CU(cudaMemcpyAsync(ctx->dCellStart, start.data(), (size_t)startInts * 4, cudaMemcpyHostToDevice, ctx->stream));
-    if (numItems)
-        CU(cudaMemcpyAsync(ctx->dCellItems, items.data(), (size_t)numItems * 16, cudaMemcpyHostToDevice, ctx->stream));
+    cull_fill_kernel<<<(cells + 127) / 128, 128, 0, s>>>(ctx->dObs, K, C, invX, invY, ctx->dCellStart, ctx->dCellItems, realItems);
+    CU(cudaGetLastError());
+    ctx->launches += 3;
     ctx->cullC = C; ctx->cullInvX = invX; ctx->cullInvY = invY; ctx->cellStartInts = startInts; ctx->numItems = numItems;
     return KGMT_OK;
 }
 
+/* obstacles are on the device in ctx->dObs[0, K) (copied there by the caller): pad to whole stream tiles, build the grid */
 static int install_obstacles(kgmt_ctx* ctx) {
     const int K = ctx->K;
-    /* the device copy is padded to whole stream tiles with boxes nothing can overlap (min = +inf, max = -inf) */
-    const size_t padded = (size_t)std::max((K + STREAM_TILE - 1) / STREAM_TILE, 1) * STREAM_TILE;
-    if (padded > ctx->obsCap) {
-        if (ctx->dObs) cudaFree(ctx->dObs);
-        CU(cudaMalloc(&ctx->dObs, padded * 16));
-        ctx->obsCap = padded;
-    }
-    {
-        std::vector<float>& h = ctx->hObsPadded;      /* outlives the asynchronous copy (set_obstacles synchronises first) */
-        h.assign(padded * 4, 0.0f);
-        if (K > 0) memcpy(h.data(), ctx->hObs.data(), std::min(ctx->hObs.size(), (size_t)K * 4) * sizeof(float));
-        for (size_t k = (size_t)K; k < padded; ++k) {
-            h[4 * k] = INFINITY; h[4 * k + 1] = INFINITY; h[4 * k + 2] = -INFINITY; h[4 * k + 3] = -INFINITY;
-        }
-        CU(cudaMemcpyAsync(ctx->dObs, h.data(), padded * 16, cudaMemcpyHostToDevice, ctx->stream));
-    }
+    const int padded = (int)ctx->obsCap;
+    if (padded > K) cull_pad_kernel<<<(padded - K + 255) / 256, 256, 0, ctx->stream>>>(ctx->dObs, K, padded);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
     int rc = build_cull_grid(ctx);
     if (rc) return rc;
     return configure(ctx);
+}
+
+/* room for K obstacles padded to whole stream tiles */
+static int ensure_obstacle_storage(kgmt_ctx* ctx, int K) {
+    const size_t padded = (size_t)std::max((K + STREAM_TILE - 1) / STREAM_TILE, 1) * STREAM_TILE;
+    if (padded != ctx->obsCap) {
+        if (ctx->dObs) cudaFree(ctx->dObs);
+        ctx->dObs = nullptr; ctx->obsCap = 0;
+        CU(cudaMalloc(&ctx->dObs, padded * 16));
+        ctx->obsCap = padded;
+    }
+    return KGMT_OK;
 }
 
 static int ensure_scratch(kgmt_ctx* ctx, size_t bytes) {
@@ -409,7 +392,7 @@ static void fill_result(const kgmt_ctx* ctx, kgmt_result* out, float ms) {
     const DevState& s = *ctx->hState;
     out->stop = s.stop; out->iterations = s.iterationsDone; out->tree_size = s.treeSize;
     out->cost_to_goal = s.costToGoal; out->goal_index = s.goalIdx; out->expansions = s.expansions;
-    out->device_ms = ms; out->kernel_launches = ctx->planLaunches;
+    out->device_ms = ms; out->kernel_launches = ctx->planLaunches; out->done_ms = ms; out->service_ms = ms;
 }
 
 typedef void (*batch_fn)(const BatchArgs);
@@ -426,7 +409,7 @@ static void free_batch(kgmt_ctx* ctx) {
     cudaFree(b.treeState); cudaFree(b.treeCtrl); cudaFree(b.stageState); cudaFree(b.stageCtrl); cudaFree(b.treeParent);
     cudaFree(b.mapSlab); cudaFree(b.blockSum); cudaFree(b.queryTicket); cudaFree(b.wsQuery); cudaFree(b.pathLen);
     cudaFree(b.chunkMask); cudaFree(b.ticket); cudaFree(b.initState); cudaFree(b.initCtrl); cudaFree(b.goalXY);
-    cudaFree(b.seeds); cudaFree(b.states); cudaFree(b.paths);
+    cudaFree(b.seeds); cudaFree(b.states); cudaFree(b.paths); cudaFree(b.launchT0);
     b = kgmt_ctx::Batch();
 }
 
@@ -530,7 +513,9 @@ void kgmt_destroy(kgmt_ctx* ctx) {
     cudaFree(ctx->stageState); cudaFree(ctx->stageCtrl);
     cudaFree(ctx->dState); cudaFree(ctx->iterLog);
     if (ctx->hState) cudaFreeHost(ctx->hState);
-    cudaFree(ctx->dObs); cudaFree(ctx->dCellStart); cudaFree(ctx->dCellItems);
+    cudaFree(ctx->dObs); cudaFree(ctx->dCellStart); cudaFree(ctx->dCellItems); cudaFree(ctx->dCullTotal);
+    if (ctx->hObsPinned) cudaFreeHost(ctx->hObsPinned);
+    if (ctx->hCullTotal) cudaFreeHost(ctx->hCullTotal);
     cudaFree(ctx->scratch); cudaFree(ctx->dParents);
     free_batch(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -625,7 +610,9 @@ int kgmt_create(const kgmt_params* p, kgmt_ctx** out) {
     ctx->dirtyCand = ctx->maxCand;
     int rc = clear_state(ctx, true);
     if (rc) return rc;
-    ctx->K = 0; ctx->hObs.clear();
+    ctx->K = 0;
+    rc = ensure_obstacle_storage(ctx, 0);
+    if (rc) return rc;
     return install_obstacles(ctx);
 }
 
@@ -645,8 +632,19 @@ int kgmt_set_seed(kgmt_ctx* ctx, uint32_t seed) {
 int kgmt_set_obstacles_host(kgmt_ctx* ctx, const float* h_aabb, int K) {
     if (!ctx || K < 0 || (K > 0 && !h_aabb)) return fail(ctx, KGMT_ERR_INVALID, "bad obstacle array");
     CU(cudaSetDevice(ctx->device));
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->hObs.assign(h_aabb, h_aabb + (size_t)4 * K);
+    CU(cudaStreamSynchronize(ctx->stream));            /* nothing in flight reads the old set or the staging buffer */
+    int rc = ensure_obstacle_storage(ctx, K);
+    if (rc) return rc;
+    if (K > 0) {
+        if ((size_t)K * 4 > ctx->hObsPinnedCap) {
+            if (ctx->hObsPinned) cudaFreeHost(ctx->hObsPinned);
+            ctx->hObsPinned = nullptr; ctx->hObsPinnedCap = 0;
+            CU(cudaHostAlloc(&ctx->hObsPinned, (size_t)K * 16 + 4096, cudaHostAllocDefault));
+            ctx->hObsPinnedCap = (size_t)K * 4 + 1024;
+        }
+        memcpy(ctx->hObsPinned, h_aabb, (size_t)K * 16);
+        CU(cudaMemcpyAsync(ctx->dObs, ctx->hObsPinned, (size_t)K * 16, cudaMemcpyHostToDevice, ctx->stream));
+    }
     ctx->K = K;
     return install_obstacles(ctx);
 }
@@ -655,8 +653,10 @@ int kgmt_set_obstacles(kgmt_ctx* ctx, const float* d_aabb, int K) {
     if (!ctx || K < 0 || (K > 0 && !d_aabb)) return fail(ctx, KGMT_ERR_INVALID, "bad obstacle array");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->hObs.resize((size_t)4 * K);
-    if (K) CU(cudaMemcpy(ctx->hObs.data(), d_aabb, (size_t)K * 16, cudaMemcpyDeviceToHost));
+    int rc = ensure_obstacle_storage(ctx, K);
+    if (rc) return rc;
+    /* device to device on the planner's stream: the caller's array is read once, here (KGMT::plan's d_obstacles, main.cu:60-62) */
+    if (K) CU(cudaMemcpyAsync(ctx->dObs, d_aabb, (size_t)K * 16, cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->K = K;
     return install_obstacles(ctx);
 }
@@ -743,11 +743,37 @@ int kgmt_plan(kgmt_ctx* ctx, const float* initial7, const float* goal7, kgmt_res
 }
 
 /* ---- batched planning: Q independent queries on the context's map (BASELINE config 4) ------------------------- */
+static int max_batch_clusters(kgmt_ctx* ctx, int cluster_size, int* out) {
+    batch_fn f = batch_entry(ctx->col);
+    CU(cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemBytes));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(TILE); cfg.dynamicSmemBytes = ctx->smemBytes; cfg.stream = ctx->stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(cluster_size * 8);
+    CU(cudaOccupancyMaxActiveClusters(out, (const void*)f, &cfg));
+    return KGMT_OK;
+}
+
+int kgmt_batch_cluster_size(kgmt_ctx* ctx, int Q) {
+    if (!ctx || Q < 1) return KGMT_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    for (int cs = 8; cs >= 4; cs >>= 1) {
+        int mc = 0;
+        int rc = max_batch_clusters(ctx, cs, &mc);
+        if (rc) return rc;
+        if (mc >= Q) return cs;
+    }
+    return 2;
+}
+
 int kgmt_plan_batch(kgmt_ctx* ctx, const float* h_inits7, const float* h_goals7, const uint32_t* h_seeds, int Q,
                     int cluster_size, kgmt_result* out, float* h_paths7, int max_path, int* h_path_len, float* device_ms) {
     if (!ctx || !h_inits7 || !h_goals7 || !h_seeds || Q < 1) return fail(ctx, KGMT_ERR_INVALID, "bad batch arguments");
+    if (cluster_size == 0) { cluster_size = kgmt_batch_cluster_size(ctx, Q); if (cluster_size < 0) return cluster_size; }
     if (cluster_size != 1 && cluster_size != 2 && cluster_size != 4 && cluster_size != 8)
-        return fail(ctx, KGMT_ERR_INVALID, "cluster_size must be 1, 2, 4 or 8");
+        return fail(ctx, KGMT_ERR_INVALID, "cluster_size must be 0 (choose), 1, 2, 4 or 8");
     if (h_paths7 && (max_path < 1 || !h_path_len)) return fail(ctx, KGMT_ERR_INVALID, "paths need max_path and path_len");
     CU(cudaSetDevice(ctx->device));
     kgmt_ctx::Batch& b = ctx->batch;
@@ -778,6 +804,7 @@ int kgmt_plan_batch(kgmt_ctx* ctx, const float* h_inits7, const float* h_goals7,
         CU(cudaMalloc(&b.goalXY, (size_t)Q * 8)); CU(cudaMalloc(&b.seeds, (size_t)Q * 4));
         CU(cudaMalloc(&b.states, (size_t)Q * sizeof(DevState)));
         CU(cudaMalloc(&b.pathLen, (size_t)Q * 4));
+        CU(cudaMalloc(&b.launchT0, 8));
         if (wantPath) CU(cudaMalloc(&b.paths, (size_t)Q * wantPath * 28));
         b.numWs = numWs; b.clusterSize = cluster_size; b.Qcap = Q; b.maxPath = wantPath; b.mapIntsStride = mapStride;
     }
@@ -807,7 +834,7 @@ int kgmt_plan_batch(kgmt_ctx* ctx, const float* h_inits7, const float* h_goals7,
     B.Q = Q; B.numWorkspaces = numWs;
     B.initState = b.initState; B.initCtrl = b.initCtrl; B.goalXY = b.goalXY; B.seeds = b.seeds; B.states = b.states;
     B.paths = wantPath ? b.paths : nullptr; B.pathLen = b.pathLen; B.maxPath = wantPath;
-    B.queryTicket = b.queryTicket; B.wsQuery = b.wsQuery;
+    B.queryTicket = b.queryTicket; B.wsQuery = b.wsQuery; B.launchT0 = b.launchT0;
     B.treeStride = T; B.mapIntsStride = mapStride; B.chunkStride = 2 * ctx->chunksCap; B.blockStride = 3 * ctx->blocksCap;
     B.stageStride = 2 * M; B.mapSlab = b.mapSlab; B.c2 = ctx->c2;
     cfg.gridDim = dim3(numWs * cluster_size);
@@ -820,6 +847,8 @@ int kgmt_plan_batch(kgmt_ctx* ctx, const float* h_inits7, const float* h_goals7,
         CU(cudaMemcpyAsync(h_paths7, b.paths, (size_t)Q * wantPath * 28, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(h_path_len, b.pathLen, (size_t)Q * 4, cudaMemcpyDeviceToHost, s));
     }
+    unsigned long long t0 = 0;
+    CU(cudaMemcpyAsync(&t0, b.launchT0, 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
@@ -830,6 +859,9 @@ int kgmt_plan_batch(kgmt_ctx* ctx, const float* h_inits7, const float* h_goals7,
             out[q].stop = d.stop; out[q].iterations = d.iterationsDone; out[q].tree_size = d.treeSize;
             out[q].cost_to_goal = d.costToGoal; out[q].goal_index = d.goalIdx; out[q].expansions = d.expansions;
             out[q].device_ms = ms; out[q].kernel_launches = 1;
+            /* the batch kernel stamps every query with the device clock: service start (pairsTested) and end (stepsDone) */
+            out[q].done_ms = d.stepsDone >= t0 ? (float)((double)(d.stepsDone - t0) * 1e-6) : ms;
+            out[q].service_ms = d.stepsDone >= d.pairsTested ? (float)((double)(d.stepsDone - d.pairsTested) * 1e-6) : ms;
         }
     return numWs;
 }

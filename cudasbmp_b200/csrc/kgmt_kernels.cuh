@@ -824,6 +824,7 @@ struct BatchArgs {
     DevState* states;             /* [Q] results */
     float* paths; int* pathLen; int maxPath;                     /* [Q][maxPath][7], [Q]; null = no paths */
     int* queryTicket; int* wsQuery;                              /* [1], [numWorkspaces] */
+    unsigned long long* launchT0;                                /* [1] globaltimer when the first CTA of the launch started */
     /* workspace strides (elements) */
     size_t treeStride, mapIntsStride, chunkStride, blockStride, stageStride;
     int* mapSlab;                 /* [ws][mapIntsStride]: R1,R1Valid,R1Invalid,R1Avail,R1Cov,R1Score x2 | R2,R2Valid,R2Invalid,R2Stamp */
@@ -864,6 +865,11 @@ __global__ void __launch_bounds__(TILE, KGMT_BATCH_MIN_CTAS) batch_kernel(const 
     A.iterLog = nullptr;
 
     const int nThreads = grp.size * TILE, gtid = grp.rank * TILE + tid;
+    if (blockIdx.x == 0 && tid == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        *B.launchT0 = t;
+    }
     for (;;) {
         if (grp.rank == 0 && tid == 0) B.wsQuery[ws] = atomicAdd(B.queryTicket, 1);
         __threadfence();
@@ -882,11 +888,21 @@ __global__ void __launch_bounds__(TILE, KGMT_BATCH_MIN_CTAS) batch_kernel(const 
         __threadfence();
         grp.sync();
         if (grp.rank == 0) begin_block(A, B.initState[q], B.initCtrl[q], sPb, 0);
+        if (grp.rank == 0 && tid == 0) {        /* per-query device clock: start (pairsTested) and end (stepsDone) of its service */
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            A.st->pairsTested = t;
+        }
         __threadfence();
         grp.sync();
         run_plan<COL, false, ClusterGroup>(A, 0x7fffffff, grp, cs);
         __threadfence();
         grp.sync();                             /* every insertion of the last iteration has landed */
+        if (grp.rank == 0 && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            A.st->stepsDone = t;
+        }
         if (B.paths && grp.rank == 0 && tid == 0) {
             /* solution back-trace, root first */
             const DevState* r = A.st;
@@ -1466,6 +1482,73 @@ __global__ void __launch_bounds__(TILE) stage_insert_kernel(const KArgs A) {
     __threadfence();
     __syncthreads();
     if (tid == 0) { st->scoreReady = S.itr; st->insertDone = S.blocksTotal; }
+}
+
+/* ------------------------------------------------- cull grid built on the device --------
+ * CSR of obstacle AABBs per cell of a C x C grid over the workspace (CollideGrid, kgmt_device.cuh).  An obstacle is filed
+ * under every cell of [cell(minx), cell(maxx)] x [cell(miny), cell(maxy)] with the SAME monotone cell() the collision
+ * walk applies to a step bbox, so culling cannot change a flag.  One thread per CELL walks the obstacle array (every
+ * thread reads the same obstacle: one broadcast load), first to count, then — after a scan — to fill in obstacle
+ * order: the structure is deterministic, no atomics, no host round trip except the item count (4 bytes). */
+__device__ __forceinline__ int cull_cell_of(float v, float inv, int C) {
+    return min(max(__float2int_rd(__fmul_rn(v, inv)), 0), C - 1);
+}
+__global__ void cull_pad_kernel(float4* obs, int K, int padded) {
+    const int k = K + blockIdx.x * blockDim.x + threadIdx.x;     /* boxes nothing can overlap (min = +inf, max = -inf) */
+    if (k < padded) obs[k] = make_float4(__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0xff800000), __int_as_float(0xff800000));
+}
+__global__ void cull_count_kernel(const float4* obs, int K, int C, float invX, float invY, int* start /* [C*C+1], zeroed */) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= C * C) return;
+    const int cy = cell / C, cx = cell - cy * C;
+    int n = 0;
+    for (int k = 0; k < K; ++k) {
+        const float4 o = __ldg(&obs[k]);
+        n += (cull_cell_of(o.x, invX, C) <= cx) & (cx <= cull_cell_of(o.z, invX, C)) &
+             (cull_cell_of(o.y, invY, C) <= cy) & (cy <= cull_cell_of(o.w, invY, C));
+    }
+    start[cell + 1] = n;
+}
+/* one CTA: start[i] = sum of the counts before cell i (in place), the padding words = the total; *total too */
+__global__ void __launch_bounds__(1024) cull_scan_kernel(int* start, int cells, int startInts, int* total) {
+    __shared__ int sWarp[32];
+    __shared__ int sCarry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { sCarry = 0; start[0] = 0; }
+    __syncthreads();
+    for (int base = 1; base <= cells; base += 1024) {
+        const int i = base + tid;
+        const int v = (i <= cells) ? start[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) sWarp[warp] = incl;
+        __syncthreads();
+        int wb = 0;
+        for (int w2 = 0; w2 < warp; ++w2) wb += sWarp[w2];
+        const int carry = sCarry;
+        if (i <= cells) start[i] = carry + wb + incl;
+        __syncthreads();
+        if (tid == 1023) sCarry = carry + wb + incl;
+        __syncthreads();
+    }
+    const int t = sCarry;
+    for (int i = cells + 1 + tid; i < startInts; i += 1024) start[i] = t;
+    if (tid == 0) *total = t;
+}
+__global__ void cull_fill_kernel(const float4* obs, int K, int C, float invX, float invY, const int* start, float4* items, int total) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell < 3)       /* the cell walk reads four entries per trip: three boxes nothing overlaps close the array */
+        items[total + cell] = make_float4(__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0xff800000), __int_as_float(0xff800000));
+    if (cell >= C * C) return;
+    const int cy = cell / C, cx = cell - cy * C;
+    int at = start[cell];
+    for (int k = 0; k < K; ++k) {
+        const float4 o = __ldg(&obs[k]);
+        if ((cull_cell_of(o.x, invX, C) <= cx) & (cx <= cull_cell_of(o.z, invX, C)) &
+            (cull_cell_of(o.y, invY, C) <= cy) & (cy <= cull_cell_of(o.w, invY, C)))
+            items[at++] = o;
+    }
 }
 
 /* ------------------------------------------------------------------ setup kernels ------ */

@@ -42,7 +42,7 @@ ABI_SYMBOLS = [
     "kgmt_set_stream", "kgmt_shard_delta_ints", "kgmt_shard_expand", "kgmt_shard_pack", "kgmt_shard_commit",
     "kgmt_peer_handle_bytes", "kgmt_peer_export", "kgmt_peer_attach", "kgmt_peer_attach_local", "kgmt_peer_expand_begin",
     "kgmt_peer_expand_end", "kgmt_peer_detach", "kgmt_peer_race",
-    "kgmt_params_from_yaml", "kgmt_stage_update_maps", "kgmt_stage_insert", "kgmt_work_counters",
+    "kgmt_params_from_yaml", "kgmt_stage_update_maps", "kgmt_stage_insert", "kgmt_work_counters", "kgmt_batch_cluster_size",
 ]
 
 
@@ -80,7 +80,7 @@ class ShardInfo(C.Structure):
 class Result(C.Structure):
     _fields_ = [("stop", C.c_int), ("iterations", C.c_int), ("tree_size", C.c_int), ("cost_to_goal", C.c_float),
                 ("goal_index", C.c_int), ("expansions", C.c_longlong), ("device_ms", C.c_float),
-                ("kernel_launches", C.c_int)]
+                ("kernel_launches", C.c_int), ("done_ms", C.c_float), ("service_ms", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -161,6 +161,7 @@ def load():
     L.kgmt_stage_update_maps.argtypes = [vp, f32p, C.POINTER(C.c_ubyte), f32p, C.POINTER(C.c_int), C.c_int]
     L.kgmt_stage_insert.argtypes = [vp, C.POINTER(IterStats)]
     L.kgmt_work_counters.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    L.kgmt_batch_cluster_size.argtypes = [vp, C.c_int]
     _lib = L
     return L
 
@@ -261,9 +262,14 @@ class KGMT:
         self.treeSize_, self.costToGoal_ = r.tree_size, r.cost_to_goal
         return r.as_dict()
 
-    def plan_batch(self, inits, goals, seeds, cluster_size=2, max_path=0):
-        """Q independent queries on this planner's map in one launch (kgmt_plan_batch).
-        Returns (results: list of dict, device_ms, paths: list of np [L,7] or None, workspaces)."""
+    def batch_cluster_size(self, Q):
+        """The cluster size plan_batch(cluster_size=0) uses for Q queries (kgmt_batch_cluster_size)."""
+        return self._ck(load().kgmt_batch_cluster_size(self._h, int(Q)))
+
+    def plan_batch(self, inits, goals, seeds, cluster_size=0, max_path=0):
+        """Q independent queries on this planner's map in one launch (kgmt_plan_batch); cluster_size 0 = chosen from Q.
+        Returns (results: list of dict incl. done_ms / service_ms per query, device_ms, paths: list of np [L,7] or None,
+        workspaces)."""
         a = _f32(inits).reshape(-1, 7)
         g = _f32(goals).reshape(-1, 7)
         sd = np.ascontiguousarray(seeds, dtype=np.uint32)

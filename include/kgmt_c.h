@@ -104,8 +104,11 @@ typedef struct kgmt_result {
     float     cost_to_goal;          /* KGMT::costToGoal_ (0 = none) */
     int       goal_index;            /* tree index of the goal node, -1 = none */
     long long expansions;            /* candidate edges checked over the whole plan */
-    float     device_ms;             /* CUDA-event time of the expansion loop */
+    float     device_ms;             /* CUDA-event time of the expansion loop (kgmt_plan_batch: of the whole launch) */
     int       kernel_launches;       /* launches of this library's kernels inside the loop */
+    float     done_ms;               /* kgmt_plan_batch: device time from the start of the launch to this query's last iteration
+                                        (its time-to-solution inside the batch, queueing included); otherwise = device_ms */
+    float     service_ms;            /* kgmt_plan_batch: device time this query occupied its cluster; otherwise = device_ms */
 } kgmt_result;
 
 /* Array ids for kgmt_export / kgmt_import.  0..12 are the thirteen CSV dumps of
@@ -177,9 +180,13 @@ int  kgmt_extract_path(kgmt_ctx* ctx, int node, float* h_rows7, int max_rows);
  * thread-block cluster of cluster_size CTAs (1, 2, 4 or 8) plans one query at a time and pulls the next from a ticket.
  * Each query gives exactly the result kgmt_plan gives for the same (init, goal, seed).  out[Q]; h_paths7 (optional)
  * receives [Q][max_path][7] solution rows, root first, h_path_len[Q] their lengths.  Returns the number of
- * concurrent workspaces used (> 0) or a negative status. */
+ * concurrent workspaces used (> 0) or a negative status.  cluster_size = 0 chooses it (kgmt_batch_cluster_size). */
 int  kgmt_plan_batch(kgmt_ctx* ctx, const float* h_inits7, const float* h_goals7, const uint32_t* h_seeds, int Q,
                      int cluster_size, kgmt_result* out, float* h_paths7, int max_path, int* h_path_len, float* device_ms);
+/* the cluster size kgmt_plan_batch uses for Q queries when asked with 0: the largest of 8, 4, 2 whose Q clusters are all
+ * resident at once (few queries: more CTAs per query shorten every query), else 2 (many queries: the measured optimum,
+ * workspaces recycled by ticket). */
+int  kgmt_batch_cluster_size(kgmt_ctx* ctx, int Q);
 
 /* ---- sharded expansion (BASELINE config 5; SURVEY.md §8e "sharded expansion") --------------------------------------
  * ONE iteration's candidates are split over `world` ranks; tree and maps are replicated on every GPU and stay

@@ -371,7 +371,7 @@ def ref_gpu():
                                      f32p]
         L.ref_gpu_plan.restype = C.c_int
         L.ref_gpu_plan.argtypes = [C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
-                                   C.c_float, f32p, f32p, f32p, C.c_int, i32p, f32p]
+                                   C.c_float, f32p, f32p, f32p, C.c_int, i32p, f32p, C.POINTER(C.c_double)]
         L.ref_gpu_last_error.restype = C.c_char_p
         _ref_gpu = L
     return _ref_gpu
@@ -399,3 +399,23 @@ def ref_gpu_expand(mode, children, tree7, frontier, maps, R1Score, N, n, R1Size,
     if rc != 0:
         raise RuntimeError("ref_gpu_expand failed rc=%d: %s" % (rc, R.ref_gpu_last_error().decode()))
     return unx, upar, gnew, ms.value
+
+
+def ref_gpu_plan(cfg, init7, goal7, obstacles):
+    """The reference's own KGMT::plan end to end (unmodified sources, sm_100a, XORWOW, time(NULL) seed):
+    dict(tree_size, cost_to_goal, plan_wall_ms = wall clock around plan() incl. its CSV dumps, inside_ms = the
+    reference's own printed 'time inside KGMT' (std::clock around its loop, KGMT.cu:82,294-295)).  cfg: the nine
+    constructor arguments under cudasbmp_b200.workloads' names."""
+    R = ref_gpu()
+    if R is None:
+        raise RuntimeError("oracle/_ref/libref_gpu.so not built")
+    i7 = np.ascontiguousarray(init7, dtype=np.float32)
+    g7 = np.ascontiguousarray(goal7, dtype=np.float32)
+    ob = np.ascontiguousarray(obstacles, dtype=np.float32).reshape(-1, 4)
+    ts, cost, ms = C.c_int(), C.c_float(), (C.c_double * 2)()
+    rc = R.ref_gpu_plan(cfg["width"], cfg["height"], cfg["N"], cfg["n"], cfg["numIterations"], cfg["maxTreeSize"],
+                        cfg["numDisc"], cfg["agentLength"], cfg["goalThreshold"], _p(i7, f32p), _p(g7, f32p), _p(ob, f32p),
+                        ob.shape[0], C.byref(ts), C.byref(cost), ms)
+    if rc != 0:
+        raise RuntimeError("ref_gpu_plan failed rc=%d" % rc)
+    return dict(tree_size=ts.value, cost_to_goal=cost.value, plan_wall_ms=ms[0], inside_ms=ms[1])

@@ -20,6 +20,12 @@
 #include <thrust/scan.h>
 #include <thrust/execution_policy.h>
 #include <thrust/device_ptr.h>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <fcntl.h>
+#include <iostream>
+#include <unistd.h>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -216,21 +222,59 @@ int ref_gpu_insert(int cap, const uint8_t* GNew, const float* unexplored, const 
 }
 
 /* The reference planner end to end (its own KGMT::plan, XORWOW, time(NULL)
- * seed): wall-clock baseline only.  obstacles = host [K][4]. */
+ * seed): timing baseline only.  obstacles = host [K][4].  planMs (may be NULL)
+ * receives {wall clock around plan() incl. its 13 CSV dumps, the reference's OWN
+ * figure "time inside KGMT" (std::clock() around its loop, KGMT.cu:82,294-295,
+ * parsed from what plan() prints), in milliseconds}.  plan() runs in a scratch
+ * directory with stdout redirected to a file, so its CSVs and prints do not
+ * land in the caller's. */
 int ref_gpu_plan(float width, float height, int N, int n, int numIterations, int maxTreeSize, int numDisc,
                  float agentLength, float goalThreshold, const float* init7, const float* goal7,
-                 const float* obstacles, int K, int* treeSizeOut, float* costOut) {
+                 const float* obstacles, int K, int* treeSizeOut, float* costOut, double* planMs) {
+    char dirT[] = "/tmp/refplan_XXXXXX";
+    char cwd[4096];
+    const bool moved = getcwd(cwd, sizeof(cwd)) && mkdtemp(dirT) && chdir(dirT) == 0;
+    fflush(stdout); std::cout.flush();
+    const int saved = dup(1);
+    const int fd = open("stdout.txt", O_CREAT | O_TRUNC | O_WRONLY, 0600);
+    if (fd >= 0) dup2(fd, 1);
     float* d_obs = dalloc<float>((size_t)4 * (K > 0 ? K : 1));
     if (K > 0) CK(cudaMemcpy(d_obs, obstacles, sizeof(float) * 4 * (size_t)K, cudaMemcpyHostToDevice));
     float i7[7], g7[7]; memcpy(i7, init7, 28); memcpy(g7, goal7, 28);
     {
         KGMT kgmt(width, height, N, n, numIterations, maxTreeSize, numDisc, agentLength, goalThreshold);
         cudaMemset(kgmt.d_costToGoal, 0, sizeof(float));   /* the reference never initialises it (App. B #4) */
+        cudaDeviceSynchronize();
+        const auto t0 = std::chrono::steady_clock::now();
         kgmt.plan(i7, g7, d_obs, K);
+        cudaDeviceSynchronize();
+        const auto t1 = std::chrono::steady_clock::now();
+        if (planMs) { planMs[0] = std::chrono::duration<double, std::milli>(t1 - t0).count(); planMs[1] = -1.0; }
         if (treeSizeOut) *treeSizeOut = kgmt.treeSize_;
         if (costOut) *costOut = kgmt.costToGoal_;
     }
     cudaFree(d_obs);
+    fflush(stdout); std::cout.flush();
+    if (saved >= 0) { dup2(saved, 1); close(saved); }
+    if (fd >= 0) close(fd);
+    if (planMs) {
+        FILE* f = fopen("stdout.txt", "r");
+        if (f) {
+            char line[512];
+            while (fgets(line, sizeof(line), f)) {
+                const char* p = strstr(line, "time inside KGMT is ");
+                if (p) planMs[1] = atof(p + 20) * 1e3;
+            }
+            fclose(f);
+        }
+    }
+    if (moved) {
+        const char* names[] = {"samples.csv", "unexploredSamples.csv", "parentRelations.csv", "uParentIdx.csv", "G.csv", "R2Avail.csv",
+                               "R1Avail.csv", "R1Valid.csv", "R2Valid.csv", "R1Invalid.csv", "R2Invalid.csv", "R1Score.csv", "R1.csv", "stdout.txt"};
+        for (const char* nm : names) unlink(nm);
+        if (chdir(cwd) != 0) return -1;
+        rmdir(dirT);
+    }
     return 0;
 }
 

@@ -34,7 +34,7 @@ for i in range(11):
     obs = np.ascontiguousarray(w.C1_OBSTACLES)
     t0 = time.perf_counter()
     rc = R.ref_gpu_plan(20.0, 20.0, 16, 8, 100, 30000, 10, 1.0, 0.5, w.C1_INIT.ctypes.data_as(f32p), w.C1_GOAL.ctypes.data_as(f32p),
-                        obs.ctypes.data_as(f32p), 5, C.byref(tsz), C.byref(cost))
+                        obs.ctypes.data_as(f32p), 5, C.byref(tsz), C.byref(cost), None)
     ts.append(time.perf_counter() - t0); sizes.append((tsz.value, cost.value))
     time.sleep(1.01)   # its seed is time(NULL)
 print("reference plan() C1 wall ms (incl. its CSV dump + allocs):", ["%.1f" % (t * 1e3) for t in ts], sizes)
