@@ -260,40 +260,47 @@ def ttfs_single(k, w, local):
     return out
 
 
+def comm_id(k, rank, dist):
+    """The NCCL unique id of the library's communicator: made by rank 0, handed to the others (here through
+    torch.distributed, which the driver's launcher has set up; a C++ host uses a pipe or a file: demos/kgmt_multi_demo.cu)."""
+    box = [k.KGMT.comm_unique_id() if rank == 0 else None]
+    if dist is not None:
+        dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
 def ttfs_multi(k, w, local, rank, world, dist, torch, races=101):
-    """Portfolio race over peer memory: every rank plans the same query with its own seed in ONE launch; the first rank
-    to reach the goal stops the others through a word in their memory (kgmt_peer_race)."""
-    from cudasbmp_b200.sharded import PeerExpander
-    out, race_id = {}, 0
+    """Portfolio over the N GPUs through the C ABI (kgmt_plan_portfolio): every rank plans the same query with its own
+    seed in ONE launch; the first rank to reach the goal stops the others through a word in their memory; the best
+    solution's result block and path are broadcast to every rank (NCCL).  Time-to-first-solution = host wall clock from a
+    common barrier until the LAST rank holds the winner's solution."""
+    out = {}
+    race_id = 0
     for name, cfg, obs, init, goal in (("c1", w.C1, w.C1_OBSTACLES, w.C1_INIT, w.C1_GOAL),
                                        ("c2", w.C2, w.c2_obstacles(1000), w.C2_INIT, w.C2_GOAL)):
         p = k.KGMT(**cfg, seed=1, device=local)
         p.set_obstacles(obs)
-        ex = PeerExpander(p)
+        p.comm_init(rank, world, comm_id(k, rank, dist))
         rows = []
         for q in range(races + 3):
             race_id += 1
-            p.set_seed(1000 * q + rank + 1)
-            torch.cuda.synchronize()
-            dist.barrier()
+            p.comm_barrier()
             t0 = time.perf_counter()
-            r = p.peer_race(init, goal, race_id)
+            win, r, path = p.plan_portfolio(init, goal, 1000 * q + 1, race_id)
             dt = (time.perf_counter() - t0) * 1e3
-            t = torch.tensor([dt if r["stop"] == 1 else 1e9, dt, float(r["stop"] == 1), r["device_ms"]], dtype=torch.float64, device="cuda")
-            g = [torch.zeros_like(t) for _ in range(world)]
-            dist.all_gather(g, t)
-            g = torch.stack(g).cpu().numpy()
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if q >= 3:
-                rows.append((g[:, 0].min(), g[:, 1].max(), g[:, 2].sum(), g[:, 3].max()))
-        rows = np.array(rows)
-        solved = rows[rows[:, 0] < 1e8]
-        if len(solved):
-            out[name] = {"races": races, "solved": int(len(solved)), "median_ms": float(np.median(solved[:, 0])),
-                         "p95_ms": float(np.percentile(solved[:, 0], 95)), "all_stopped_median_ms": float(np.median(rows[:, 1])),
-                         "winners_per_race_mean": float(rows[:, 2].mean())}
-        dist.barrier()
-        ex.close(); p.close()
-    out["clock"] = "host wall from a common barrier to the first rank returning a solution (kgmt_peer_race, seed = 1000*race + rank + 1)"
+                rows.append((float(t[0]), win, r["device_ms"], len(path)))
+        solved = [x for x in rows if x[1] >= 0]
+        if solved:
+            tt = sorted(x[0] for x in solved)
+            out[name] = {"races": races, "solved": len(solved), "median_ms": statistics.median(tt), "p95_ms": tt[int(0.95 * (len(tt) - 1))],
+                         "winner_device_ms_median": statistics.median(x[2] for x in solved),
+                         "path_nodes_median": statistics.median(x[3] for x in solved)}
+        p.comm_destroy(); p.close()
+    out["clock"] = ("host wall from a common barrier until the slowest rank holds the winning solution and path "
+                    "(kgmt_plan_portfolio: peer-memory race + NCCL min-reduce + broadcast), seed = 1000*race + 1 + rank")
     return out
 
 
@@ -317,125 +324,114 @@ def bench_c3(k, plan_mod, wl3, local):
 
 
 def bench_c4(k, w, local, rank, world, dist, torch, Q=1024, reps=5):
-    """Config 4: ONE fixed batch of Q queries on the reference demo map, sharded contiguously over the ranks; every rank
-    plans its shard in one launch (kgmt_plan_batch: a thread-block cluster per query) and the fixed-size result table is
-    all-reduced.  Strong scaling: the same Q at every N.  Reported: queries/s and aggregate expansions/s on the slowest
-    rank's device time and on wall time (barrier to barrier, result gather included), median / p95 time-to-solution of a
-    query (device clock from the start of its rank's launch to the query's last iteration)."""
-    from cudasbmp_b200.multi import shard_range
+    """Config 4: ONE fixed batch of Q queries on the reference demo map, sharded contiguously over the ranks
+    (kgmt_plan_batch_sharded: every rank plans its shard in one launch, a thread-block cluster per query; the fixed-size
+    result rows are all-gathered by NCCL inside the library).  Strong scaling: the same Q at every N.  Reported:
+    queries/s and aggregate expansions/s on the slowest rank's device time and on wall time (barrier to every rank holding
+    all Q results), median / p95 time-to-solution of a query (device clock from the start of its rank's launch to the
+    query's last iteration)."""
     inits, goals = w.random_queries(Q, w.C1_OBSTACLES)
     seeds = np.arange(Q, dtype=np.uint32)
-    lo, hi = shard_range(Q, rank, world)
     p = k.KGMT(**w.C1, seed=1, device=local)
     p.set_obstacles(w.C1_OBSTACLES)
-    cs = p.batch_cluster_size(hi - lo)
-    p.plan_batch(inits[lo:hi], goals[lo:hi], seeds[lo:hi], cluster_size=cs)             # warm-up: allocations, code upload
+    p.comm_init(rank, world, comm_id(k, rank, dist))
+    per = (Q + world - 1) // world
+    cs = p.batch_cluster_size(per)
+    p.plan_batch_sharded(inits, goals, seeds, cluster_size=cs)                          # warm-up: allocations, code upload
     best = None
     for _ in range(reps):
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
+        p.comm_barrier()
         t0 = time.perf_counter()
-        res, ms, _, ws = p.plan_batch(inits[lo:hi], goals[lo:hi], seeds[lo:hi], cluster_size=cs)
-        table = np.zeros((Q, 4), dtype=np.float64)
-        for i, r in enumerate(res):
-            table[lo + i] = (r["stop"], r["expansions"], r["tree_size"], r["done_ms"])
-        t = torch.from_numpy(table).cuda()
-        tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        table = t.cpu().numpy()
-        torch.cuda.synchronize()
+        res, dev_ms = p.plan_batch_sharded(inits, goals, seeds, cluster_size=cs)
         wall = time.perf_counter() - t0
         tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
-        wall, dev_ms = float(tw[0]), float(tm[0])
+        wall = float(tw[0])
         if best is None or wall < best["wall_ms"] * 1e-3:
-            solved = table[:, 0] == 1
-            tt = np.sort(table[solved, 3])
-            best = {"queries": Q, "gpus": world, "cluster_size": cs, "workspaces_per_gpu": ws, "solved": int(solved.sum()),
+            solved = [r for r in res if r["stop"] == 1]
+            tt = sorted(r["done_ms"] for r in solved)
+            exp = float(sum(r["expansions"] for r in res))
+            best = {"queries": Q, "gpus": world, "cluster_size": cs, "solved": len(solved),
                     "device_ms_max": dev_ms, "wall_ms": wall * 1e3, "queries_per_s_device": Q / dev_ms * 1e3,
-                    "queries_per_s_wall": Q / wall, "expansions": float(table[:, 1].sum()),
-                    "expansions_per_s_device": float(table[:, 1].sum()) / dev_ms * 1e3,
-                    "expansions_per_s_wall": float(table[:, 1].sum()) / wall,
-                    "time_to_solution_median_ms": float(np.median(tt)) if len(tt) else None,
-                    "time_to_solution_p95_ms": float(tt[int(0.95 * (len(tt) - 1))]) if len(tt) else None}
-    p.close()
+                    "queries_per_s_wall": Q / wall, "expansions": exp,
+                    "expansions_per_s_device": exp / dev_ms * 1e3, "expansions_per_s_wall": exp / wall,
+                    "time_to_solution_median_ms": statistics.median(tt) if tt else None,
+                    "time_to_solution_p95_ms": tt[int(0.95 * (len(tt) - 1))] if tt else None,
+                    "service_ms_median": statistics.median(r["service_ms"] for r in solved) if solved else None}
+    p.comm_destroy(); p.close()
     return best
 
 
-def bench_c5(k, w, local, rank, world, dist, torch, logs=(20, 22, 24, 26), reps=3, P=32768):
+def bench_c5(k, K, w, local, rank, world, dist, torch, logs=(20, 22, 24, 26), reps=3, P=32768):
     """Config 5: ONE iteration of M = 2^log candidates (P parents in free space of the config-2 map, each expanded M/P
-    times), sharded over the ranks with the exchange over peer memory (the library's kernels) and, for comparison, over
-    NCCL; at N = 1 the cooperative kernel and the sharded kernel sequence.  Times: CUDA events, max over ranks."""
-    from cudasbmp_b200.sharded import PeerExpander, ShardedExpander
+    times), sharded over the ranks through kgmt_expand_sharded with its three exchanges: fused into the persistent kernel
+    (peer memory), the multi-launch peer sequence, NCCL all-gather / all-reduce (compute and exchange time separately).
+    At N = 1 also the single-GPU cooperative kernel.  CUDA-event times, max over ranks, best of `reps`.
+    Plus whole config-2 PLANS with sharded iterations (kgmt_plan_sharded), median of 5."""
     obs = w.c2_obstacles(1000)
     parents = w.random_parents(P, obs, seed=7)
     Mmax = 1 << max(logs)
     p = k.KGMT(**dict(w.C1, maxTreeSize=Mmax + P, numIterations=4), seed=5, device=local, max_candidates=Mmax)
     p.set_obstacles(obs)
+    p.comm_init(rank, world, comm_id(k, rank, dist))
     out = {"parents": P, "K": 1000, "gpus": world, "points": []}
 
-    def mx(v):
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+    def mx(*v):
+        t = torch.tensor(list(v), dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0])
+        return [float(x) for x in t.tolist()]
 
-    def one(ex, M, rep):
-        p.set_seed(5 + rep)
-        p.seed_frontier(parents, w.C2_GOAL)
-        p.set_children(M // P)
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        return ex.iterate()
-
-    peer = PeerExpander(p, timing=True)
+    names = {K.EXCHANGE_FUSED: "fused", K.EXCHANGE_PEER_LAUNCHES: "peer_launches", K.EXCHANGE_NCCL: "nccl"}
     for lg in logs:
         M = 1 << lg
         pt = {"log2M": lg, "M": M}
-        best = None
-        for rep in range(reps + 1):
-            st = one(peer, M, rep)
-            tot = mx(st["total_ms"])
-            if rep > 0 and (best is None or tot < best):
-                best = tot
-                pt["accepted"] = st["accepted"]
-        pt["peer_total_ms"] = best
-        pt["peer_expansions_per_s"] = M / best * 1e3
-        out["points"].append(pt)
-    peer.close()
-    if dist is not None:
-        dist.barrier()
-    nccl = ShardedExpander(p, timing=True)
-    for pt in out["points"]:
-        M = pt["M"]
-        best = None
-        for rep in range(reps + 1):
-            st = one(nccl, M, rep)
-            comp, comm = mx(st["compute_ms"]), mx(st["comm_ms"])
-            if rep > 0 and (best is None or comp + comm < best[0] + best[1]):
-                best = (comp, comm, st["comm_bytes"])
-        pt["nccl_compute_ms"], pt["nccl_exchange_ms"], pt["nccl_exchange_bytes"] = best
-        pt["nccl_expansions_per_s"] = M / (best[0] + best[1]) * 1e3
-    p.set_stream(None)
-    if world == 1:
-        for pt in out["points"]:
-            M = pt["M"]
+        for ex, nm in names.items():
+            best = None
+            for rep in range(reps + 1):
+                p.set_seed(5 + rep)
+                p.seed_frontier(parents, w.C2_GOAL)
+                p.set_children(M // P)
+                p.comm_barrier()
+                st = p.expand_sharded(ex, timing=True)
+                comp, exch = mx(st["compute_ms"], st["exchange_ms"])
+                if rep > 0 and (best is None or comp + exch < best[0] + best[1]):
+                    best = (comp, exch, st["exchange_bytes"], st["accepted"])
+            pt["accepted"] = best[3]
+            if ex == K.EXCHANGE_NCCL:
+                pt["nccl_compute_ms"], pt["nccl_exchange_ms"], pt["nccl_exchange_bytes"] = best[0], best[1], best[2]
+                pt["nccl_expansions_per_s"] = M / (best[0] + best[1]) * 1e3
+            else:
+                pt[nm + "_ms"] = best[0]
+                pt[nm + "_expansions_per_s"] = M / best[0] * 1e3
+        if world == 1:
             ms = []
             for rep in range(reps):
                 p.set_seed(6 + rep)
                 p.seed_frontier(parents, w.C2_GOAL); p.set_children(M // P)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s = torch.cuda.ExternalStream(p.stream)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(s); p.iterate(); e1.record(s); torch.cuda.synchronize()
                 ms.append(e0.elapsed_time(e1))
             pt["cooperative_kernel_ms"] = min(ms)
             pt["cooperative_expansions_per_s"] = M / min(ms) * 1e3
-    p.close()
+        out["points"].append(pt)
+    p.comm_destroy(); p.close()
+    # whole config-2 plans, every iteration's candidates split over the ranks, one persistent kernel per rank
+    q = k.KGMT(**w.C2, seed=1, device=local)
+    q.set_obstacles(obs)
+    q.comm_init(rank, world, comm_id(k, rank, dist))
+    q.plan_sharded(w.C2_INIT, w.C2_GOAL)
+    ms, exp, tree = [], 0, 0
+    for s in range(5):
+        q.set_seed(1 + s)
+        q.comm_barrier()
+        r = q.plan_sharded(w.C2_INIT, w.C2_GOAL)
+        ms.append(mx(r["device_ms"])[0]); exp += r["expansions"]; tree = r["tree_size"]
+    out["c2_plan_sharded"] = {"plans": 5, "median_ms": statistics.median(ms), "expansions_per_s": exp / (sum(ms) * 1e-3),
+                              "tree_size_last": tree, "what": "kgmt_plan_sharded: whole config-2 plans, tree bit-identical to kgmt_plan"}
+    q.comm_destroy(); q.close()
     return out
 
 
@@ -594,14 +590,14 @@ def main():
                 plan.set_seed(seed_of(args.warmup + s, j))
                 r = plan.plan(wl["init"], wl["goal"])
                 e2e_exp += r["expansions"]
-                d2h += 128
+                d2h += 4 + 152                                # cull-grid item count + the planner's scalar block
                 if r["stop"] == 1:
                     path = plan.extract_path()
-                    d2h += 128 + 4 + len(path) * 28          # state block + length + the AoS-7 rows
+                    d2h += 4 + 152                                # cull-grid item count + the planner's scalar block + 4 + len(path) * 28          # state block + length + the AoS-7 rows
         barrier()
         e2e_s = time.perf_counter() - t1
     cfgd = plan.config()
-    h2d = pps * (obs_host.nbytes + cfgd["cull_items"] * 16 + (cfgd["cull_cells"] ** 2 + 4) * 4 + 56 + 128)
+    h2d = pps * (obs_host.nbytes + 56)        # the obstacle set + init/goal rows; the cull grid is built on the device
 
     # ---- the other named configurations (extra keys of the line)
     extra = {}
@@ -626,13 +622,14 @@ def main():
             if world > 1:
                 # the same fixed batch on ONE GPU of this box (rank 0 alone), so the line carries its own strong-scaling base
                 one = bench_c4(k, w, local, 0, 1, None, torch) if rank == 0 else None
+                torch.cuda.synchronize()
                 dist.barrier()
                 extra["c4"]["one_gpu_same_box"] = one
         except Exception as e:
             extra["c4"] = {"error": repr(e)}
     if "c5" not in skip:
         try:
-            extra["c5"] = bench_c5(k, w, local, rank, world, dist, torch)
+            extra["c5"] = bench_c5(k, K, w, local, rank, world, dist, torch)
         except Exception as e:
             extra["c5"] = {"error": repr(e)}
     extra_s = time.perf_counter() - t_extra

@@ -21,8 +21,11 @@
 
 using namespace kgmt;
 
+struct kgmt_comm_state;              /* kgmt_comm.inl */
+
 struct kgmt_ctx {
     kgmt_params p;
+    kgmt_comm_state* comm = nullptr;   /* NCCL communicator + exchange buffers (kgmt_comm_init) */
     int device = 0, numSMs = 0, maxCand = 0, c1 = 0;
     size_t c2 = 0;
     float R1Size = 0.f, R2Size = 0.f;
@@ -89,6 +92,7 @@ struct kgmt_ctx {
     /* sharded expansion (kgmt_shard_*) */
     int* shardPrefix = nullptr; int* shardTotal = nullptr; int* hShardTotal = nullptr;   /* [blocksCap], [1], pinned [1] */
     int shardBlkLo = 0, shardBlkHi = 0, shardAccepted = -1, shardGrid = 0;
+    int fusedGrid = 0;                 /* persistent grid of expand_sharded_kernel (cooperative) */
     /* sharded expansion over peer memory (kgmt_peer_*) */
     struct Peer {
         int rank = -1, world = 0, seq = 0; bool ipc = false, inFlight = false;
@@ -152,6 +156,16 @@ static shard_fn shard_entry(int col) {
         case COL_GRID_GLOBAL: return shard_expand_kernel<COL_GRID_GLOBAL>;
         case COL_BRUTE_SMEM: return shard_expand_kernel<COL_BRUTE_SMEM>;
         default: return shard_expand_kernel<COL_BRUTE_GLOBAL>;
+    }
+}
+
+typedef void (*fused_fn)(const KArgs, const KArgs, const PeerArgs, int, int, size_t);
+static fused_fn fused_entry(int col) {
+    switch (col) {
+        case COL_GRID_SMEM: return expand_sharded_kernel<COL_GRID_SMEM>;
+        case COL_GRID_GLOBAL: return expand_sharded_kernel<COL_GRID_GLOBAL>;
+        case COL_BRUTE_SMEM: return expand_sharded_kernel<COL_BRUTE_SMEM>;
+        default: return expand_sharded_kernel<COL_BRUTE_GLOBAL>;
     }
 }
 
@@ -223,6 +237,14 @@ static int configure(kgmt_ctx* ctx) {
         int o = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, sf, TILE, ctx->smemBytes));
         ctx->shardGrid = std::max(o, 1) * ctx->numSMs;
+    }
+    {
+        const void* ff = (const void*)fused_entry(col);
+        const size_t fsm = (col == COL_BRUTE_STREAM) ? histBytes : ctx->smemBytes;
+        CU(cudaFuncSetAttribute(ff, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+        int o = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, ff, TILE, fsm));
+        ctx->fusedGrid = std::max(o, 1) * ctx->numSMs;
     }
     if (occ < 1) return fail(ctx, KGMT_ERR_CUDA, "expand kernel does not fit on an SM (smem %zu B)", ctx->smemBytes);
     ctx->gridMax = occ * ctx->numSMs;
@@ -504,6 +526,7 @@ void kgmt_destroy(kgmt_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    kgmt_comm_destroy(ctx);
     kgmt_peer_detach(ctx);
     cudaFree(ctx->treeState); cudaFree(ctx->treeCtrl); cudaFree(ctx->treeParent);
     cudaFree(ctx->mapSlab); cudaFree(ctx->mapSlabCkpt);
@@ -1003,7 +1026,8 @@ static int peer_alloc(kgmt_ctx* ctx) {
         cudaFuncAttributes fa;
         const void* fns[] = {(const void*)shard_reset_kernel, (const void*)shard_entry(ctx->col), (const void*)shard_prefix_kernel,
                              (const void*)peer_counts_kernel, (const void*)peer_pack_kernel, (const void*)peer_reduce_kernel,
-                             (const void*)peer_barrier_kernel, (const void*)recount_cov_kernel, (const void*)peer_finalize_kernel};
+                             (const void*)peer_barrier_kernel, (const void*)recount_cov_kernel, (const void*)peer_finalize_kernel,
+                             (const void*)fused_entry(ctx->col), (const void*)begin_kernel};
         for (const void* f : fns) CU(cudaFuncGetAttributes(&fa, f));
     }
     return KGMT_OK;
@@ -1187,6 +1211,91 @@ int kgmt_peer_expand_end(kgmt_ctx* ctx, kgmt_iter_stats* out) {
         out->candidates = s.lastM; out->accepted = s.lastAccepted; out->tree_size = s.treeSize; out->stop = s.stop;
         out->cost_to_goal = s.costToGoal; out->goal_index = s.goalIdx;
     }
+    return KGMT_OK;
+}
+
+/* ---- the fused form: compute + exchange in ONE persistent cooperative kernel per rank ---------------------------- */
+static int launch_fused(kgmt_ctx* ctx, int maxIters) {
+    kgmt_ctx::Peer& pr = ctx->peer;
+    const KArgs A = make_args(ctx);
+    const KArgs As = make_shard_args(ctx, (int*)pr.block);
+    pr.args.seq = pr.seq;
+    int seq0 = pr.seq;
+    size_t c2 = ctx->c2;
+    CU(cudaMemsetAsync(pr.plan, 0, sizeof(PeerPlan), ctx->stream));
+    /* resident CTAs per SM: the same knob as the single-GPU loop (params.reserved[1]); never more CTAs than can be co-resident */
+    int grid = ctx->fusedGrid;
+    if (ctx->p.reserved[1] > 0) grid = std::min(grid, ctx->p.reserved[1] * ctx->numSMs);
+    const size_t histBytes = ctx->useHist ? (((size_t)2 * ctx->c1 * 4 + 15) & ~(size_t)15) : 0;
+    size_t smem = (ctx->col == COL_BRUTE_STREAM) ? histBytes : ctx->smemBytes;
+    PeerArgs P = pr.args;
+    void* args[] = {(void*)&A, (void*)&As, (void*)&P, (void*)&maxIters, (void*)&seq0, (void*)&c2};
+    CU(cudaLaunchCooperativeKernel((const void*)fused_entry(ctx->col), dim3(grid), dim3(TILE), args, smem, ctx->stream));
+    CU(cudaMemcpyAsync(pr.hPlan, pr.plan, sizeof(PeerPlan), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->launches += 1;
+    ctx->planLaunches += 1;
+    return KGMT_OK;
+}
+
+static int finish_fused(kgmt_ctx* ctx, int itersBefore) {
+    kgmt_ctx::Peer& pr = ctx->peer;
+    int rc = fetch_state(ctx);
+    if (rc) return rc;
+    if (pr.hPlan->err) return fail(ctx, KGMT_ERR_COMM, "a peer did not arrive within 5 s (rank %d of %d)", pr.rank, pr.world);
+    pr.seq += ctx->hState->iterationsDone - itersBefore;          /* one exchange per iteration, the same count on every rank */
+    return KGMT_OK;
+}
+
+/* up to `count` sharded iterations in ONE launch per rank (every attached rank calls it for the same iterations) */
+int kgmt_peer_expand_iterations(kgmt_ctx* ctx, int count, kgmt_iter_stats* out) {
+    if (!ctx || count < 1) return KGMT_ERR_INVALID;
+    kgmt_ctx::Peer& pr = ctx->peer;
+    if (pr.rank < 0) return fail(ctx, KGMT_ERR_STATE, "kgmt_peer_expand_iterations before kgmt_peer_attach");
+    if (!ctx->begun) return fail(ctx, KGMT_ERR_STATE, "kgmt_peer_expand_iterations before kgmt_begin / kgmt_seed_frontier");
+    if (pr.inFlight) return fail(ctx, KGMT_ERR_STATE, "an exchange of kgmt_peer_expand_begin is still in flight");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->hState->stop == STOP_RUNNING) {
+        const int before = ctx->hState->iterationsDone;
+        int rc = launch_fused(ctx, count);
+        if (rc) return rc;
+        rc = finish_fused(ctx, before);
+        if (rc) return rc;
+    }
+    if (out) {
+        const DevState& s = *ctx->hState;
+        out->iteration = s.lastItr; out->mode = s.lastMode; out->children = s.lastChildren; out->frontier = s.lastFrontier;
+        out->candidates = s.lastM; out->accepted = s.lastAccepted; out->tree_size = s.treeSize; out->stop = s.stop;
+        out->cost_to_goal = s.costToGoal; out->goal_index = s.goalIdx;
+    }
+    return KGMT_OK;
+}
+
+/* KGMT::plan with every iteration's candidates split over the attached ranks: root insertion on every rank (same seed,
+ * same root: identical replicas), then the whole loop in one persistent launch per rank.  Every rank returns the same
+ * result and holds the same tree as kgmt_plan on one GPU. */
+int kgmt_peer_plan(kgmt_ctx* ctx, const float* initial7, const float* goal7, kgmt_result* out) {
+    if (!ctx || !initial7 || !goal7) return fail(ctx, KGMT_ERR_INVALID, "null initial/goal");
+    kgmt_ctx::Peer& pr = ctx->peer;
+    if (pr.rank < 0) return fail(ctx, KGMT_ERR_STATE, "kgmt_peer_plan before kgmt_peer_attach");
+    if (pr.inFlight) return fail(ctx, KGMT_ERR_STATE, "an exchange of kgmt_peer_expand_begin is still in flight");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (ctx->begun) { int rc = clear_state(ctx, false, true); if (rc) return rc; }
+    memcpy(ctx->goal, goal7, sizeof(ctx->goal));
+    const KArgs A = make_args(ctx);
+    begin_kernel<<<1, TILE, 0, ctx->stream>>>(A, make_float4(initial7[0], initial7[1], initial7[2], initial7[3]),
+                                             make_float4(initial7[4], initial7[5], initial7[6], 0.f), ctx->hState->forceChildren);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    ctx->planLaunches = 1;
+    { int rc = launch_fused(ctx, 0x7fffffff); if (rc) return rc; }
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->begun = true;
+    int rc = finish_fused(ctx, 0);
+    if (rc) return rc;
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (out) fill_result(ctx, out, ms);
     return KGMT_OK;
 }
 
@@ -1632,3 +1741,5 @@ int kgmt_get_config(const kgmt_ctx* ctx, int* out8) {
 }
 
 }  /* extern "C" */
+
+#include "kgmt_comm.inl"

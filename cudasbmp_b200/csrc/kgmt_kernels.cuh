@@ -1164,7 +1164,8 @@ __global__ void __launch_bounds__(TILE) shard_finalize_kernel(const KArgs A, con
  * Replicas stay bit-identical to the single-GPU run for the same reason as with NCCL: rank-major = candidate order. */
 constexpr int PEER_MAX = 16;
 struct PeerMail { unsigned long long goal; int count; int seq1; int seq2; int pad; };      /* 24 B -> padded to 32 */
-struct PeerPlan { unsigned long long goalLocal, goalGlobal; int base, total, err, pad; int counts[PEER_MAX]; };
+struct PeerPlan { unsigned long long goalLocal, goalGlobal; int base, total, err, pad; int counts[PEER_MAX];
+                  int ready1, ready2, pad2[2]; };   /* fused kernel: exchange seq whose counts / goal are in (release/acquire, gpu scope) */
 struct PeerArgs {
     int rank, world, seq;
     float4* treeState[PEER_MAX]; float4* treeCtrl[PEER_MAX]; int* treeParent[PEER_MAX];
@@ -1350,6 +1351,300 @@ __global__ void __launch_bounds__(TILE) peer_finalize_kernel(const KArgs A, cons
     __syncthreads();
     if (tid < COPIED_WORDS && tid != THRESHOLD_WORD) reinterpret_cast<int*>(st)[tid] = reinterpret_cast<const int*>(&S)[tid];
     if (tid == 0) { st->scoreReady = S.itr; st->insertDone = S.blocksTotal; }
+}
+
+/* ------------------ sharded PLANS in one persistent kernel per rank: compute + exchange fused ------
+ * The multi-launch sequence above costs nine launches and two host-visible round trips per iteration.  Here ONE
+ * cooperative launch per rank runs any number of iterations (kgmt_peer_plan: the whole plan) and does the exchange
+ * itself over peer memory (NVLink / NVSwitch), with the grid barrier as the only local synchronisation:
+ *
+ *   phase A        stages 2-5a on this rank's contiguous range of scan blocks (chunks by ticket inside the range);
+ *                  counter increments into this rank's delta slab, accepted rows ballot-compacted into staging
+ *   grid barrier 1
+ *   counts         CTA 0 / warp 0: system fence, this rank's accepted count into every peer's mailbox (release.sys), wait
+ *                  for every peer's count -> base row, total; released to the other CTAs through plan->ready1
+ *   pack           accepted rows of this rank, candidate order, stored STRAIGHT INTO EVERY RANK'S TREE at
+ *                  treeSize + base + local position — all-gather and insertion are one pass of stores over NVLink
+ *   reduce         this rank's 1/world share of the counter cells: sum of every rank's delta (peer loads), new counter
+ *                  values and first-reached stamps into every rank's maps (reduce-scatter + all-gather, peer stores)
+ *   grid barrier 2
+ *   goal           CTA 0 / warp 0: system fence, this rank's goal candidate to every peer, wait for every peer ->
+ *                  every pack / reduce store of every rank has landed here; global goal minimum; plan->ready2
+ *   finish         all CTAs: zero the delta slab, recount R1Cov from the stamps, advance the planner scalars (every
+ *                  CTA on its own copy, as in run_plan)
+ *   grid barrier 3, then one CTA scores the next iteration while the others already run its phase A
+ *
+ * A peer is never more than one exchange ahead (it needs this rank's count to finish exchange i + 1, and this rank
+ * posts that only after it has consumed everything of exchange i), so one mailbox slot per peer suffices; the sequence
+ * numbers only grow.  A peer that does not arrive within 5 s sets plan->err and every CTA leaves the loop together.
+ * Replicas stay bit-identical to a single-GPU run: rank-major row order == candidate order (tests/test_gpu_sharded.py). */
+__device__ __forceinline__ bool peer_wait_ge(const int* p, int want) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    unsigned ns = 32;
+    while ((int)(ld_acquire_sys_s32(p) - want) < 0) {
+        __nanosleep(ns); if (ns < 1024) ns <<= 1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > 5000000000ull) return false;
+    }
+    return true;
+}
+/* every thread of the CTA waits until the local word has reached `want` (written by CTA 0 with a gpu-scope release) */
+__device__ __forceinline__ void cta_wait_flag(const int* p, int want) {
+    if (threadIdx.x == 0) { unsigned ns = 32; while ((int)(ld_acquire_s32(p) - want) < 0) { __nanosleep(ns); if (ns < 512) ns <<= 1; } }
+    __syncthreads();
+}
+
+template <int COL>
+__global__ void __launch_bounds__(TILE, 3) expand_sharded_kernel(const KArgs A, const KArgs As, const PeerArgs P, int maxIters, int seq0, size_t c2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t sBar;
+    __shared__ int sRed[WARPS];
+    __shared__ int sScan[WARPS];
+    __shared__ float sP[1024];
+    __shared__ DevState S;
+    __shared__ int sGoalSlot;
+    cg::grid_group grid = cg::this_grid();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nCta = (int)gridDim.x, cta = (int)blockIdx.x;
+    ColSet cs = stage_collision<COL>(A, smem_raw, &sBar);
+    int* hV = cs.hV; int* hI = cs.hI;
+    DevState* st = A.st;
+    PeerPlan* plan = P.plan;
+    const DynParams dyn{A.W, A.H, A.L, A.numDisc};
+    const int rank = P.rank, world = P.world;
+    if (tid < COPIED_WORDS) reinterpret_cast<int*>(&S)[tid] = __ldcg(reinterpret_cast<const int*>(st) + tid);
+    __syncthreads();
+    const int totalWarps = nCta * WARPS;
+    const int gw = cta * WARPS + warp;
+    const size_t c1 = (size_t)A.c1;
+    const size_t deltaInts = 4 * c1 + 4 * c2;
+    const int nn = A.n * A.n;
+
+    for (int iter = 0; iter < maxIters; ++iter) {
+        if (S.stop != STOP_RUNNING) break;
+        const int seq = seq0 + iter + 1;
+        IterView it = make_view(A, S);
+        const int numBlocks = (it.numChunks + BLK_CHUNKS - 1) / BLK_CHUNKS;
+        const int bBase = numBlocks / world, bRem = numBlocks % world;
+        const int bLo = rank * bBase + min(rank, bRem), bHi = bLo + bBase + (rank < bRem ? 1 : 0);
+        const int cLo = bLo * BLK_CHUNKS, cHi = min(bHi * BLK_CHUNKS, it.numChunks);
+
+        /* ---- phase A on [cLo, cHi): first chunk by position, the rest by ticket */
+        if (A.useHist) for (int c = tid; c < 2 * A.c1; c += TILE) hV[c] = 0;
+        __syncthreads();
+        {
+            bool scoresOk = false;
+            unsigned* ticket = A.ticket + (it.itr % 3);
+            int c = cLo + gw, t = 0;
+            while (c < cHi) {
+                if (lane == 0) t = (int)atomicAdd(ticket, 1u);
+                if (COL == COL_GRID_SMEM)        expand_chunk<CollideGrid, false, true>(As, it, dyn, cs.gridS, c, lane, hV, hI, scoresOk);
+                else if (COL == COL_GRID_GLOBAL) expand_chunk<CollideGrid, false, true>(As, it, dyn, cs.gridG, c, lane, hV, hI, scoresOk);
+                else if (COL == COL_BRUTE_SMEM)  expand_chunk<CollideSmemAll, false, true>(As, it, dyn, cs.allS, c, lane, hV, hI, scoresOk);
+                else                             expand_chunk<CollideSmemAll, false, true>(As, it, dyn, cs.allG, c, lane, hV, hI, scoresOk);
+                c = cLo + __shfl_sync(0xffffffffu, t, 0);
+            }
+        }
+        __syncthreads();
+        if (A.useHist) {
+            for (int r = tid; r < A.c1; r += TILE) {
+                const int v = hV[r], iv = hI[r];
+                if (v | iv) {
+                    atomicAdd(&As.R1[r], v + iv);
+                    if (v) atomicAdd(&As.R1Valid[r], v);
+                    if (iv) atomicAdd(&As.R1Invalid[r], iv);
+                }
+            }
+        }
+        grid.sync();                                                    /* 1: ballots, block sums, deltas of this rank are final */
+
+        /* ---- counts: CTA 0 / warp 0 talks to the peers */
+        if (cta == 0 && warp == 0) {
+            int mine = 0;
+            for (int b = bLo + lane; b < bHi; b += 32) mine += __ldcg(&it.blockSum[b]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+            if (lane == 0) { plan->goalLocal = ~0ull; plan->goalGlobal = ~0ull; }
+            __threadfence_system();
+            bool ok = true;
+            int cnt = 0;
+            if (lane < world) {
+                PeerMail* m = P.mail[lane] + rank;
+                m->count = mine;
+                __threadfence_system();
+                st_release_sys_s32(&m->seq1, seq);
+                const PeerMail* in = P.mail[rank] + lane;
+                ok = peer_wait_ge(&in->seq1, seq);
+                cnt = *(volatile const int*)&in->count;
+            }
+            const bool bad = __any_sync(0xffffffffu, !ok);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t2; }
+            if (lane == rank) plan->base = incl - cnt;
+            if (lane == 31) plan->total = incl;
+            if (bad && lane == 0) plan->err = 1;
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release_s32(&plan->ready1, seq);
+        }
+        cta_wait_flag(&plan->ready1, seq);
+        if (*(volatile const int*)&plan->err) break;
+        __threadfence_system();                                         /* peers' deltas are read below */
+        const int base = *(volatile const int*)&plan->base, total = *(volatile const int*)&plan->total;
+
+        /* ---- pack: this rank's accepted rows into every replica's tree (updateG on every replica, KGMT.cu:555-591) */
+        for (int blk = bLo + cta; blk < bHi; blk += nCta) {
+            int m2 = 0;
+            for (int b = bLo + tid; b < blk; b += TILE) m2 += __ldcg(&it.blockSum[b]);
+            const int prefix = block_sum(m2, sRed);
+            const int c = blk * BLK_CHUNKS + tid;
+            const unsigned mask = (c < it.numChunks) ? __ldcg(&it.chunkMask[c]) : 0u;
+            const int cnt = __popc(mask);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t2; }
+            __syncthreads();
+            if (lane == 31) sScan[warp] = incl;
+            __syncthreads();
+            int warpBase = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < WARPS; ++w2) if (w2 < warp) warpBase += sScan[w2];
+            const int W = __shfl_sync(0xffffffffu, incl, 31);
+            const int c0 = blk * BLK_CHUNKS + warp * 32;
+            const int q0g = base + prefix + warpBase;
+            for (int q0 = 0; q0 < W; q0 += 32) {
+                const int q = q0 + lane;
+                int i = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int v = __shfl_sync(0xffffffffu, incl, i + step - 1);
+                    if (v <= q) i += step;
+                }
+                i = min(i, 31);
+                const unsigned m = __shfl_sync(0xffffffffu, mask, i);
+                const int excl = __shfl_sync(0xffffffffu, incl - cnt, i);
+                if (q < W) {
+                    const int r = q - excl;
+                    const int bit = nth_set_bit(m, r);
+                    const int ci = c0 + i;
+                    const int slot = ci * CHUNK + bit;
+                    const float4 x = __ldcg(&it.stageState[ci * CHUNK + r]);
+                    const float4 u = __ldcg(&it.stageCtrl[ci * CHUNK + r]);
+                    const int row = q0g + q;
+                    const int dst = it.treeSize + row;
+                    const int parent = it.frontierStart + slot / it.children;
+                    for (int p = 0; p < world; ++p) {
+                        P.treeState[p][dst] = x;
+                        P.treeCtrl[p][dst] = u;
+                        P.treeParent[p][dst] = parent;
+                    }
+                    if (in_goal(x.x, x.y, A.goalX, A.goalY, A.goalR))
+                        atomicMin(&plan->goalLocal, ((unsigned long long)__float_as_uint(u.w) << 32) | (unsigned)row);
+                }
+            }
+            __syncthreads();
+        }
+
+        /* ---- reduce: this rank's share of the delta index space, new values into every replica's maps */
+        {
+            const size_t per = deltaInts / world, extra = deltaInts % world;
+            const size_t lo = rank * per + min((size_t)rank, extra), hi = lo + per + ((size_t)rank < extra ? 1 : 0);
+            const unsigned stampNew = (unsigned)it.itr + 1u;
+            const int* mine = P.mapSlab[rank];
+            for (size_t idx = lo + (size_t)cta * TILE + tid; idx < hi; idx += (size_t)nCta * TILE) {
+                int sum = 0;
+                for (int p = 0; p < world; ++p) sum += __ldcg(&P.delta[p][idx]);
+                if (sum == 0) continue;
+                size_t at; int val; size_t at2 = (size_t)-1;
+                if (idx < 4 * c1) {
+                    const size_t k = idx / c1, i = idx - k * c1;
+                    if (k == 3) continue;
+                    at = k * c1 + i; val = mine[at] + sum;
+                    if (k == 1) at2 = 3 * c1 + i;                              /* R1Avail, KGMT.cu:400 */
+                } else {
+                    const size_t j = idx - 4 * c1, k = j / c2, i = j - k * c2;
+                    at = 7 * c1 + k * c2 + i;
+                    if (k == 3) { if (mine[at] != 0) continue; val = (int)stampNew; }
+                    else val = mine[at] + sum;
+                }
+                for (int p = 0; p < world; ++p) {
+                    P.mapSlab[p][at] = val;
+                    if (at2 != (size_t)-1) P.mapSlab[p][at2] = 1;
+                }
+            }
+        }
+        __threadfence_system();
+        grid.sync();                                                    /* 2: every pack / reduce store of this rank is issued */
+
+        /* ---- goal exchange = the barrier across the GPUs */
+        if (cta == 0 && warp == 0) {
+            __threadfence_system();
+            bool ok = true;
+            unsigned long long g = ~0ull;
+            if (lane < world) {
+                PeerMail* m = P.mail[lane] + rank;
+                m->goal = *(volatile unsigned long long*)&plan->goalLocal;
+                __threadfence_system();
+                st_release_sys_s32(&m->seq2, seq);
+                const PeerMail* in = P.mail[rank] + lane;
+                ok = peer_wait_ge(&in->seq2, seq);
+                g = *(volatile const unsigned long long*)&in->goal;
+            }
+            const bool bad = __any_sync(0xffffffffu, !ok);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const unsigned long long t2 = __shfl_xor_sync(0xffffffffu, g, o); g = t2 < g ? t2 : g; }
+            if (lane == 0) { plan->goalGlobal = g; if (bad) plan->err = 1; }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release_s32(&plan->ready2, seq);
+        }
+        cta_wait_flag(&plan->ready2, seq);
+        if (*(volatile const int*)&plan->err) break;
+        __threadfence_system();                                         /* rows and map values written by the peers are read from here on */
+
+        /* ---- finish: zero the delta slab, recount R1Cov, advance the planner scalars */
+        {
+            int4* z = reinterpret_cast<int4*>(P.delta[rank]);
+            const size_t n4 = deltaInts / 4;                            /* c1 and c2 are multiples of 1: deltaInts = 4 (c1 + c2) */
+            for (size_t i = (size_t)cta * TILE + tid; i < n4; i += (size_t)nCta * TILE) z[i] = make_int4(0, 0, 0, 0);
+            for (int c = cta * WARPS + warp; c < A.c1; c += totalWarps) {
+                int cntS = 0;
+                for (int i = lane; i < nn; i += 32) cntS += (__ldcg(&A.R2Stamp[(size_t)c * nn + i]) != 0u);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cntS += __shfl_xor_sync(0xffffffffu, cntS, o);
+                if (lane == 0) A.R1Cov[c] = cntS;
+            }
+        }
+        if (tid == 0) {
+            const unsigned long long gb = *(volatile unsigned long long*)&plan->goalGlobal;   /* (cost bits << 32) | global row */
+            const bool hadGoal = S.costToGoal != 0.0f;
+            const int treeSize0 = S.treeSize;
+            advance_state(A, S, total, gb);
+            sGoalSlot = (!hadGoal && S.costToGoal != 0.0f) ? treeSize0 + (int)(unsigned)gb : -1;
+            if (cta == 0 && sGoalSlot >= 0) st->goalIdx = sGoalSlot;
+        }
+        __syncthreads();
+        /* recycle the ticket / block sums used two iterations from now; scalars to global memory */
+        if (cta == (nCta > 1 ? nCta - 2 : 0)) {
+            const int r = (it.itr + 2) % 3;
+            for (int b = tid; b < A.blocksCap; b += TILE) A.blockSum[(size_t)r * A.blocksCap + b] = 0;
+            if (tid == 0) A.ticket[r] = (unsigned)totalWarps;
+        }
+        if (cta == 0 && tid < COPIED_WORDS && tid != THRESHOLD_WORD)
+            reinterpret_cast<int*>(st)[tid] = reinterpret_cast<const int*>(&S)[tid];
+        __threadfence();
+        grid.sync();                                                    /* 3: delta zeroed, R1Cov recounted */
+        if (cta == nCta - 1 && S.stop == STOP_RUNNING) {
+            scores_block(A, sP, A.R1Score[S.itr & 1]);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release_s32(&st->scoreReady, S.itr);
+        }
+    }
+    /* the insertion bookkeeping of the single-GPU loop is not used here: leave it consistent for a later kgmt_expand_* */
+    if (cta == 0 && tid == 0) st->insertDone = S.blocksTotal;
 }
 
 /* -------------------------------------------- stages 2-4 alone (parity / sweeps) -------

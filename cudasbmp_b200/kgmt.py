@@ -43,7 +43,11 @@ ABI_SYMBOLS = [
     "kgmt_peer_handle_bytes", "kgmt_peer_export", "kgmt_peer_attach", "kgmt_peer_attach_local", "kgmt_peer_expand_begin",
     "kgmt_peer_expand_end", "kgmt_peer_detach", "kgmt_peer_race",
     "kgmt_params_from_yaml", "kgmt_stage_update_maps", "kgmt_stage_insert", "kgmt_work_counters", "kgmt_batch_cluster_size",
+    "kgmt_peer_expand_iterations", "kgmt_peer_plan",
+    "kgmt_comm_unique_id", "kgmt_comm_init", "kgmt_comm_destroy", "kgmt_comm_barrier", "kgmt_comm_rank", "kgmt_comm_world",
+    "kgmt_plan_batch_sharded", "kgmt_plan_portfolio", "kgmt_expand_sharded", "kgmt_plan_sharded",
 ]
+EXCHANGE_FUSED, EXCHANGE_PEER_LAUNCHES, EXCHANGE_NCCL = 0, 1, 2
 
 
 class KgmtError(RuntimeError):
@@ -162,6 +166,19 @@ def load():
     L.kgmt_stage_insert.argtypes = [vp, C.POINTER(IterStats)]
     L.kgmt_work_counters.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     L.kgmt_batch_cluster_size.argtypes = [vp, C.c_int]
+    L.kgmt_peer_expand_iterations.argtypes = [vp, C.c_int, C.POINTER(IterStats)]
+    L.kgmt_peer_plan.argtypes = [vp, f32p, f32p, C.POINTER(Result)]
+    L.kgmt_comm_unique_id.argtypes = [vp]
+    L.kgmt_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.kgmt_comm_destroy.argtypes = [vp]
+    L.kgmt_comm_barrier.argtypes = [vp]
+    L.kgmt_comm_rank.argtypes = [vp]
+    L.kgmt_comm_world.argtypes = [vp]
+    L.kgmt_plan_batch_sharded.argtypes = [vp, f32p, f32p, C.POINTER(C.c_uint32), C.c_int, C.c_int, C.POINTER(Result), f32p]
+    L.kgmt_plan_portfolio.argtypes = [vp, f32p, f32p, C.c_uint32, C.c_int, C.POINTER(Result), C.POINTER(C.c_int), f32p, C.c_int,
+                                      C.POINTER(C.c_int)]
+    L.kgmt_expand_sharded.argtypes = [vp, C.c_int, C.POINTER(IterStats), f32p]
+    L.kgmt_plan_sharded.argtypes = [vp, f32p, f32p, C.POINTER(Result)]
     _lib = L
     return L
 
@@ -442,6 +459,84 @@ class KGMT:
         self._ck(load().kgmt_peer_race(self._h, i.ctypes.data_as(f32p), g.ctypes.data_as(f32p), int(race_id), C.byref(r)))
         self.treeSize_, self.costToGoal_ = r.tree_size, r.cost_to_goal
         return r.as_dict()
+
+    def peer_iterate_fused(self, count=1):
+        """Up to `count` sharded iterations in ONE persistent launch (compute + exchange fused); every rank calls it."""
+        st = IterStats()
+        self._ck(load().kgmt_peer_expand_iterations(self._h, int(count), C.byref(st)))
+        self.treeSize_, self.costToGoal_ = st.tree_size, st.cost_to_goal
+        return st.as_dict()
+
+    def peer_plan(self, initial, goal):
+        """KGMT::plan with every iteration's candidates split over the attached ranks, one persistent launch per rank."""
+        i, g = _f32(initial, 7), _f32(goal, 7)
+        r = Result()
+        f32p = C.POINTER(C.c_float)
+        self._ck(load().kgmt_peer_plan(self._h, i.ctypes.data_as(f32p), g.ctypes.data_as(f32p), C.byref(r)))
+        self.treeSize_, self.costToGoal_ = r.tree_size, r.cost_to_goal
+        return r.as_dict()
+
+    # ------------------------------------------------------------------ communicator (NCCL inside the library)
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL unique id (rank 0 creates it; hand it to every rank by any transport)."""
+        buf = (C.c_ubyte * 128)()
+        if load().kgmt_comm_unique_id(buf) != OK:
+            raise KgmtError("kgmt_comm_unique_id failed (NCCL not loadable?)")
+        return bytes(buf)
+
+    def comm_init(self, rank, world, unique_id):
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        self._ck(load().kgmt_comm_init(self._h, int(rank), int(world), buf))
+
+    def comm_destroy(self):
+        self._ck(load().kgmt_comm_destroy(self._h))
+
+    def comm_barrier(self):
+        self._ck(load().kgmt_comm_barrier(self._h))
+
+    def expand_sharded(self, exchange=EXCHANGE_FUSED, timing=False):
+        """One sharded iteration across the communicator's ranks; with timing also (compute_ms, exchange_ms, bytes)."""
+        st = IterStats()
+        ms = (C.c_float * 3)()
+        self._ck(load().kgmt_expand_sharded(self._h, int(exchange), C.byref(st), ms if timing else None))
+        self.treeSize_, self.costToGoal_ = st.tree_size, st.cost_to_goal
+        d = st.as_dict()
+        if timing:
+            d.update(compute_ms=ms[0], exchange_ms=ms[1], exchange_bytes=ms[2])
+        return d
+
+    def plan_sharded(self, initial, goal):
+        i, g = _f32(initial, 7), _f32(goal, 7)
+        r = Result()
+        f32p = C.POINTER(C.c_float)
+        self._ck(load().kgmt_plan_sharded(self._h, i.ctypes.data_as(f32p), g.ctypes.data_as(f32p), C.byref(r)))
+        self.treeSize_, self.costToGoal_ = r.tree_size, r.cost_to_goal
+        return r.as_dict()
+
+    def plan_batch_sharded(self, inits, goals, seeds, cluster_size=0):
+        """Config 4 across the communicator: returns (results of ALL Q queries, max device ms over the ranks)."""
+        a = _f32(inits).reshape(-1, 7)
+        g = _f32(goals).reshape(-1, 7)
+        sd = np.ascontiguousarray(seeds, dtype=np.uint32)
+        Q = a.shape[0]
+        res = (Result * Q)()
+        ms = C.c_float()
+        f32p = C.POINTER(C.c_float)
+        self._ck(load().kgmt_plan_batch_sharded(self._h, a.ctypes.data_as(f32p), g.ctypes.data_as(f32p),
+                                                sd.ctypes.data_as(C.POINTER(C.c_uint32)), Q, int(cluster_size), res, C.byref(ms)))
+        return [r.as_dict() for r in res], ms.value
+
+    def plan_portfolio(self, initial, goal, base_seed, race_id, max_rows=256):
+        """Same query, seed base_seed + rank per rank, first solution wins; returns (winner rank or -1, the winner's
+        result dict, its path [L, 7]) on every rank."""
+        i, g = _f32(initial, 7), _f32(goal, 7)
+        r, win, plen = Result(), C.c_int(-1), C.c_int(0)
+        path = np.zeros((max_rows, 7), dtype=np.float32)
+        f32p = C.POINTER(C.c_float)
+        self._ck(load().kgmt_plan_portfolio(self._h, i.ctypes.data_as(f32p), g.ctypes.data_as(f32p), int(base_seed) & 0xFFFFFFFF,
+                                            int(race_id), C.byref(r), C.byref(win), path.ctypes.data_as(f32p), max_rows, C.byref(plen)))
+        return win.value, r.as_dict(), path[:min(plen.value, max_rows)].copy()
 
     def peer_detach(self):
         self._ck(load().kgmt_peer_detach(self._h))

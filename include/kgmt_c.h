@@ -230,10 +230,51 @@ int  kgmt_peer_attach_local(kgmt_ctx* ctx, int rank, int world, kgmt_ctx* const*
 int  kgmt_peer_expand_begin(kgmt_ctx* ctx);
 int  kgmt_peer_expand_end(kgmt_ctx* ctx, kgmt_iter_stats* out);
 int  kgmt_peer_detach(kgmt_ctx* ctx);
+/* The same exchange FUSED with the expansion into one persistent cooperative kernel per rank (compute + collective in one
+ * launch, the grid barrier as the only local synchronisation, no host round trip between iterations): up to `count`
+ * sharded iterations, or a whole plan (root insertion on every rank + every iteration until the planner stops — KGMT::plan,
+ * KGMT.cu:80-317, with each iteration's candidates split over the ranks).  Every attached rank makes the same call;
+ * every rank ends with the same scalars and a tree bit-identical to the single-GPU one. */
+int  kgmt_peer_expand_iterations(kgmt_ctx* ctx, int count, kgmt_iter_stats* out);
+int  kgmt_peer_plan(kgmt_ctx* ctx, const float* initial7, const float* goal7, kgmt_result* out);
 /* portfolio race between the attached ranks: same query, own seed per rank (kgmt_set_seed), ONE launch per rank; the
  * first rank to reach the goal stops the others through a word in their memory; they return KGMT_PEER_SOLVED.
  * race_id > 0, growing from race to race (KGMT::plan has no counterpart: KGMT.cu:118-259 is a single-GPU loop). */
 int  kgmt_peer_race(kgmt_ctx* ctx, const float* initial7, const float* goal7, int race_id, kgmt_result* out);
+/* ---- multi-GPU communicator: one process per GPU on one NVSwitch box, host side in C/C++ (no Python needed) ---------
+ * The reference is single-GPU (KGMT::plan, KGMT.cu:80-317, called by demos/main.cu:62); these calls are what its main()
+ * would use with one process per GPU.  NCCL (loaded with dlopen on first use) carries the setup and the result
+ * collectives; the data path of the sharded expansion runs over peer memory inside the library's own kernels.
+ *   kgmt_comm_unique_id   rank 0: a 128-byte NCCL unique id; the host program hands it to every rank (pipe, file, MPI ...)
+ *   kgmt_comm_init        NCCL communicator on the context's device; all-gather of the peer-memory handles; attach;
+ *                         barrier.  After it every kgmt_peer_* call and the calls below are available.
+ *   kgmt_plan_batch_sharded  BASELINE config 4: Q independent queries, contiguous shards over the ranks, every rank plans
+ *                         its shard with kgmt_plan_batch; out_all[Q] (identical on every rank) by one NCCL all-gather
+ *   kgmt_plan_portfolio   the SAME query with seed base_seed + rank on every rank, ONE launch per rank; the first rank
+ *                         to reach the goal stops the others through peer memory (kgmt_peer_race); the lowest-cost
+ *                         solution's result block and path are broadcast to every rank (NCCL) — first-solution broadcast
+ *   kgmt_expand_sharded   BASELINE config 5: ONE iteration's candidates split over the ranks.  exchange selects how the
+ *                         accepted rows / counters travel; ms3 (optional) = {compute ms, exchange ms, exchange bytes}
+ *                         (the fused kernel cannot separate them: {total ms, 0, 0})
+ *   kgmt_plan_sharded     whole plans with sharded iterations in one persistent kernel per rank (= kgmt_peer_plan) */
+typedef enum kgmt_exchange {
+    KGMT_EXCHANGE_FUSED = 0,          /* compute + exchange in one persistent kernel per rank, peer memory (NVLink) */
+    KGMT_EXCHANGE_PEER_LAUNCHES = 1,  /* the same exchange as a sequence of kernels (kgmt_peer_expand_begin / _end) */
+    KGMT_EXCHANGE_NCCL = 2            /* all-gather(counts), all-gather(rows), all-reduce(counter deltas) by NCCL */
+} kgmt_exchange;
+#define KGMT_COMM_ID_BYTES 128
+int  kgmt_comm_unique_id(void* out_id128);
+int  kgmt_comm_init(kgmt_ctx* ctx, int rank, int world, const void* nccl_unique_id128);
+int  kgmt_comm_destroy(kgmt_ctx* ctx);
+int  kgmt_comm_barrier(kgmt_ctx* ctx);
+int  kgmt_comm_rank(const kgmt_ctx* ctx);
+int  kgmt_comm_world(const kgmt_ctx* ctx);
+int  kgmt_plan_batch_sharded(kgmt_ctx* ctx, const float* h_inits7, const float* h_goals7, const uint32_t* h_seeds, int Q,
+                             int cluster_size, kgmt_result* out_all, float* device_ms_max);
+int  kgmt_plan_portfolio(kgmt_ctx* ctx, const float* initial7, const float* goal7, uint32_t base_seed, int race_id,
+                         kgmt_result* out_winner, int* winner_rank, float* h_path7, int max_rows, int* path_len);
+int  kgmt_expand_sharded(kgmt_ctx* ctx, int exchange, kgmt_iter_stats* out, float* ms3);
+int  kgmt_plan_sharded(kgmt_ctx* ctx, const float* initial7, const float* goal7, kgmt_result* out);
 /* launch on the caller's CUDA stream (cudaStream_t) instead of the context's own; NULL restores it.  Lets the calls
  * above order with NCCL collectives enqueued on the same stream without extra synchronisation. */
 int  kgmt_set_stream(kgmt_ctx* ctx, void* cuda_stream);

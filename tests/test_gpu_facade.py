@@ -70,3 +70,45 @@ def test_data_driven_demo(tmp_path):
     p = K.KGMT(**w.C1, seed=5, record_candidates=True)
     r = p.plan(w.C1_INIT, w.C1_GOAL, w.C1_OBSTACLES)
     assert ("Tree size %d" % r["tree_size"]) in out.stdout
+
+
+def _multi_demo(args, tmp_path):
+    exe = os.path.join(BIN, "kgmt_multi_demo")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    return subprocess.run([exe] + [str(a) for a in args], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+
+
+def test_cpp_multi_gpu_demo_one_rank(tmp_path):
+    """The C++ multi-GPU host program (one process per GPU, NCCL unique id through a shared page, kgmt_comm_init,
+    kgmt_plan_sharded / kgmt_plan_batch_sharded / kgmt_plan_portfolio / kgmt_expand_sharded) with a world of ONE: every
+    collective and the fused kernel run against themselves; the sharded plan must equal kgmt_plan."""
+    out = _multi_demo([1], tmp_path)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "multi-GPU demo ok (world 1)" in out.stdout and "identical 1" in out.stdout
+    assert "plan_portfolio world 1: winner rank 0" in out.stdout
+    for ex in (0, 1, 2):
+        assert ("expand_sharded world 1 exchange %d: iteration 4" % ex) in out.stdout, out.stdout
+    # the three exchanges expand the same four iterations into the same tree
+    sizes = set(l.split("tree ")[1].split()[0] for l in out.stdout.splitlines() if l.startswith("expand_sharded"))
+    assert len(sizes) == 1, out.stdout
+
+
+def test_cpp_multi_gpu_demo_all_gpus(tmp_path):
+    """The same program over every GPU of the box (>= 2, else skipped), reference demo map and the config-2 map."""
+    import torch
+    G = torch.cuda.device_count()
+    if G < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from cudasbmp_b200 import workloads as w
+    out = _multi_demo([G], tmp_path)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert ("multi-GPU demo ok (world %d)" % G) in out.stdout and "identical 1" in out.stdout
+    csv = tmp_path / "c2.csv"
+    with open(csv, "w") as f:
+        for o in w.c2_obstacles(1000):
+            f.write(",".join("%.9g" % v for v in o) + "\n")
+    out = _multi_demo([G, csv, 16, 32, 1 << 20], tmp_path)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "identical 1" in out.stdout

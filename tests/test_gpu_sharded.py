@@ -246,3 +246,86 @@ def test_c5_full_size_one_iteration_property():
     assert int(ma[K.ARR_R1].sum()) == int(ma[K.ARR_R1VALID].sum()) + int(ma[K.ARR_R1INVALID].sum()) <= M + P
     assert int(ma[K.ARR_R1].sum()) >= int(0.8 * M)
     assert sa["accepted"] == sa["tree_size"] - P and (np.diff(pa[P:]) >= 0).all() and pa[P:].max() < P
+
+
+# ------------------------------------------------- compute + exchange FUSED in one persistent kernel per rank
+def _cfgs(name):
+    if name == "c1":
+        return w.C1, w.C1_OBSTACLES, w.C1_INIT, w.C1_GOAL
+    return dict(w.C2, maxTreeSize=200000), w.c2_obstacles(1000), w.C2_INIT, w.C2_GOAL
+
+
+@pytest.mark.parametrize("cfgname", ["c1", "c2small"])
+def test_fused_sharded_kernel_one_rank_equals_single_gpu(cfgname):
+    """kgmt_peer_plan / kgmt_peer_expand_iterations with a world of one (two cooperative kernels cannot share a GPU, so
+    a single-GPU box can only run the fused kernel against itself): counts and goal through its own mailbox, rows packed
+    into its own tree, deltas reduced from its own slab — every code path of the fused kernel except the remote addresses.
+    Whole plans and stepped iterations must equal kgmt_plan / kgmt_expand_iteration bit for bit."""
+    cfg, obs, init, goal = _cfgs(cfgname)
+    ref = K.KGMT(**cfg, seed=17); ref.set_obstacles(obs)
+    p = K.KGMT(**cfg, seed=17); p.set_obstacles(obs)
+    p.peer_attach_local(0, [p])
+    for seed in (17, 18):
+        ref.set_seed(seed); p.set_seed(seed)
+        want, got = ref.plan(init, goal), p.peer_plan(init, goal)
+        for k in ("stop", "iterations", "tree_size", "cost_to_goal", "goal_index", "expansions"):
+            assert want[k] == got[k], (seed, k, want[k], got[k])
+        assert got["kernel_launches"] == 2
+        _same_state(ref, p, want["tree_size"])
+        if want["stop"] == 1:
+            np.testing.assert_array_equal(ref.extract_path(), p.extract_path())
+    # stepped: 1, then 2 iterations per launch; then the single-GPU loop carries on from the fused kernel's state
+    ref.set_seed(19); p.set_seed(19)
+    ref.begin(init, goal); p.begin(init, goal)
+    assert ref.iterate() == p.peer_iterate_fused(1)
+    ref.iterate(); a = ref.iterate()
+    assert a == p.peer_iterate_fused(2)
+    _same_state(ref, p, a["tree_size"])
+    if a["stop"] == 0:
+        assert ref.iterate() == p.iterate()
+        assert ref.iterate() == p.peer_iterate_fused(1)
+        _same_state(ref, p, ref.result()["tree_size"])
+    p.peer_detach()
+
+
+@pytest.mark.parametrize("cfgname", ["c1", "c2small", "c2"])
+def test_fused_sharded_plans_on_several_gpus(cfgname):
+    """Whole sharded plans on every GPU of the box (>= 2, else skipped): one context per GPU in this process, wired with
+    kgmt_peer_attach_local (peer access over NVLink), one host thread per rank calling kgmt_peer_plan.  Every replica
+    must hold the single-GPU tree, links, costs and maps bit for bit, and every rank must report the same result."""
+    import threading
+    G = min(torch.cuda.device_count(), 8)
+    if G < 2:
+        pytest.skip("needs at least 2 GPUs")
+    cfg, obs, init, goal = (w.C2, w.c2_obstacles(1000), w.C2_INIT, w.C2_GOAL) if cfgname == "c2" else _cfgs(cfgname)
+    ref = K.KGMT(**cfg, seed=23, device=0); ref.set_obstacles(obs)
+    want = ref.plan(init, goal)
+    ranks = []
+    for g in range(G):
+        p = K.KGMT(**cfg, seed=23, device=g); p.set_obstacles(obs)
+        ranks.append(p)
+    for g, p in enumerate(ranks):
+        p.peer_attach_local(g, ranks)
+    got, errs = [None] * G, []
+
+    def run(g):
+        try:
+            got[g] = ranks[g].peer_plan(init, goal)
+        except Exception as e:            # noqa: BLE001
+            errs.append((g, repr(e)))
+    for rep in range(2):                                  # the second plan re-uses the attached state (sequence numbers go on)
+        th = [threading.Thread(target=run, args=(g,)) for g in range(G)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(60)
+        assert not errs, errs
+        for g in range(G):
+            for k in ("stop", "iterations", "tree_size", "cost_to_goal", "goal_index", "expansions"):
+                assert want[k] == got[g][k], (g, k, want[k], got[g][k])
+    for p in ranks:
+        _same_state(ref, p, want["tree_size"])
+        if want["stop"] == 1:
+            np.testing.assert_array_equal(ref.extract_path(), p.extract_path())
+    for p in ranks:
+        p.peer_detach()
