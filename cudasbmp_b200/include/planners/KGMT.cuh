@@ -35,6 +35,24 @@ class KGMT {
         p.max_tree_size = maxTreeSize; p.num_disc = numDisc; p.agent_length = agentLength; p.goal_threshold = goalThreshold;
         p.seed = seed_;                       /* the reference seeds from time(NULL) inside plan() (KGMT.cu:111) */
         p.record_candidates = 1;              /* keep unexploredSamples.csv / uParentIdx.csv meaningful (KGMT.cu:300,302) */
+        create(p);
+    }
+    /* not in the reference: every parameter, including the car model's control ranges the reference hard-codes in
+     * statePropagator.cu:17-19 (e.g. filled by kgmt_params_from_yaml from a systems/car.yaml) */
+    explicit KGMT(const kgmt_params& params)
+        : numIterations_(params.num_iterations), maxTreeSize_(params.max_tree_size), numDisc_(params.num_disc), treeSize_(0),
+          width_(params.width), height_(params.height), costToGoal_(0.0f), agentLength_(params.agent_length), R1Threshold_(0.0f),
+          goalThreshold_(params.goal_threshold), N_(params.N), n_(params.n) {
+        seed_ = params.seed;
+        timeSeed_ = false;
+        create(params);
+    }
+    KGMT(const KGMT&) = delete;
+    KGMT& operator=(const KGMT&) = delete;
+    ~KGMT() { kgmt_destroy(ctx_); }
+
+  private:
+    void create(const kgmt_params& p) {
         const int rc = kgmt_create(&p, &ctx_);
         if (rc != KGMT_OK) {
             std::printf("KGMT: kgmt_create failed (%d): %s\n", rc, kgmt_last_error(ctx_));
@@ -45,9 +63,8 @@ class KGMT {
         R1Size_ = kgmt_r1_size(ctx_);         /* KGMT.cu:13 */
         R2Size_ = kgmt_r2_size(ctx_);         /* KGMT.cu:14 */
     }
-    KGMT(const KGMT&) = delete;
-    KGMT& operator=(const KGMT&) = delete;
-    ~KGMT() { kgmt_destroy(ctx_); }
+
+  public:
 
     /* KGMT::plan, KGMT.cu:80-317.  initial / goal: host float[7]; d_obstacles: DEVICE float[obstaclesCount][4],
      * caller-owned (main.cu:60-64).  Prints what the reference prints and leaves its 13 CSV files in the cwd.

@@ -4,8 +4,11 @@
  * configurations/{init,goal,numR1,R2}/*.csv are never opened and systems/car.yaml is empty.  This demo
  * reads all of them when present, falls back to the main.cu literals otherwise, plans through the
  * reference-compatible KGMT class, prints the solution path (§8f rank 2) and leaves the 13 CSV files in the cwd.
+ * The car model — wheelbase, integration steps and the control ranges the reference hard-codes in
+ * statePropagator.cu:17-19 — comes from <config_dir>/../systems/car.yaml (or the 5th argument) through
+ * kgmt_params_from_yaml; the reference ships that file EMPTY, which leaves its literals in force.
  *
- *   kgmt_demo [config_dir=../configurations] [seed] [maxTreeSize] [numIterations]
+ *   kgmt_demo [config_dir=../configurations] [seed] [maxTreeSize] [numIterations] [car.yaml]
  */
 #include <cstdio>
 #include <cstdlib>
@@ -52,9 +55,27 @@ int main(int argc, char** argv) {
     std::printf("init (%g, %g) goal (%g, %g) N %d n %d obstacles %d seed %u\n", initial[0], initial[1], goal[0], goal[1], N,
                 n, numObstacles, seed);
 
-    KGMT kgmt(width, height, N, n, numIterations, maxTreeSize, numDisc, agentLength, goalThreshold);
+    kgmt_params params;
+    kgmt_default_params(&params);
+    params.width = width; params.height = height; params.N = N; params.n = n; params.num_iterations = numIterations;
+    params.max_tree_size = maxTreeSize; params.num_disc = numDisc; params.agent_length = agentLength;
+    params.goal_threshold = goalThreshold; params.seed = seed; params.record_candidates = 1;
+    {
+        const std::string yaml = argc > 5 ? argv[5] : dir + "/../systems/car.yaml";
+        std::ifstream probe(yaml);
+        if (probe) {
+            int badLine = 0;
+            if (kgmt_params_from_yaml(yaml.c_str(), &params, &badLine) != KGMT_OK) {
+                std::printf("car model %s: cannot parse line %d\n", yaml.c_str(), badLine);
+                return 3;
+            }
+            std::printf("car model %s: L %g numDisc %d a [%g, %g] steer [%g, %g] duration [%g, %g]\n", yaml.c_str(),
+                        params.agent_length, params.num_disc, params.accel_min, params.accel_max, params.steer_min,
+                        params.steer_max, params.duration_min, params.duration_max);
+        }
+    }
+    KGMT kgmt(params);
     if (!kgmt.context()) return 2;
-    kgmt.setSeed(seed);
     float* d_obstacles = nullptr;
     CUDA_ERROR_CHECK(cudaMalloc(&d_obstacles, sizeof(float) * 4 * (numObstacles > 0 ? numObstacles : 1)));
     if (numObstacles)

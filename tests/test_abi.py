@@ -71,6 +71,21 @@ def test_car_yaml_loader(lib, tmp_path):
     assert lib.kgmt_params_from_yaml(os.fsencode(str(wrong)), C.byref(p), C.byref(bad)) == -1 and bad.value == 2
 
 
+def test_shipped_car_yaml_is_the_reference_model(lib):
+    """systems/car.yaml of this repo spells out the literals of statePropagator.cu:17-19: loading it must give the same
+    EFFECTIVE control transform as the defaults (accelerations and durations are narrowed to float, steering stays double)."""
+    import numpy as np
+    import cudasbmp_b200 as k
+    p, d = k.kgmt.default_params(), k.kgmt.default_params()
+    bad = C.c_int(0)
+    assert lib.kgmt_params_from_yaml(os.fsencode(os.path.join(ROOT, "systems", "car.yaml")), C.byref(p), C.byref(bad)) == 0, bad.value
+    f = np.float32
+    assert (p.agent_length, p.num_disc) == (d.agent_length, d.num_disc)
+    assert (f(p.accel_max - p.accel_min), f(p.accel_min)) == (f(d.accel_max - d.accel_min), f(d.accel_min))
+    assert (p.steer_max - p.steer_min, p.steer_min) == (d.steer_max - d.steer_min, d.steer_min)
+    assert (f(p.duration_max - p.duration_min), f(p.duration_min)) == (f(d.duration_max - d.duration_min), f(d.duration_min))
+
+
 def test_no_cpu_fallback(lib):
     import torch
     import cudasbmp_b200 as k
