@@ -166,7 +166,11 @@ int main(int argc, char** argv) {
     std::vector<pid_t> kids;
     for (int r = 0; r < world; ++r) {
         pid_t pid = fork();
-        if (pid == 0) _exit(run_rank(r, world, sh, obs, N, n, maxTree, init, goal));
+        if (pid == 0) {
+            const int rc = run_rank(r, world, sh, obs, N, n, maxTree, init, goal);
+            fflush(nullptr);                      /* _exit does not flush stdio */
+            _exit(rc);
+        }
         kids.push_back(pid);
     }
     int bad = 0;

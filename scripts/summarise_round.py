@@ -50,10 +50,13 @@ with open(os.path.join(P, tag + "_bench_baselines_timeline.txt"), "w") as f:
         except OSError:
             return "(missing)\n"
     f.write("# gpurun pass %s, one B200; host CPU: %s" % (tag, tail(tag + "_smi.log", 2).replace("\n", " ") + "\n"))
-    f.write("## bench.py (default: C2, 20 steps, 3 warm-up)\n" + tail(tag + "_bench.log"))
+    f.write("## bench.py (default: C2, 20 steps of 64 plans, 3 warm-up)\n" + tail(tag + "_bench.log"))
     f.write("## bench.py --impl reference --steps 3 --warmup 1\n" + tail(tag + "_bench_ref.log"))
     f.write("## baseline A: the reference's own CUDA kernels recompiled for sm_100a (scripts/baseline_ref_gpu.py)\n")
-    f.write("".join(l for l in open(os.path.join(G, tag + "_baselineA.log")) if l.startswith(("c1 P", "c2 P", "reference plan", "ours plan"))))
+    if os.path.exists(os.path.join(G, tag + "_baselineA.log")):
+        f.write("".join(l for l in open(os.path.join(G, tag + "_baselineA.log")) if l.startswith(("c1 P", "c2 P", "reference plan", "ours plan"))))
+    else:
+        f.write("(in the bench line: same_population / ref_cuda_baseline / ttfs.reference_ms)\n")
     f.write("## per-iteration device timeline of one C2 plan (scripts/iter_profile.py timeline)\n" + open(os.path.join(G, tag + "_timeline.log")).read())
     f.write("## pytest -m gpu\n" + tail(tag + "_pytest.log", 2))
 print(json.dumps(out, indent=1))
