@@ -1705,6 +1705,23 @@ float kgmt_r2_size(const kgmt_ctx* ctx) { return ctx ? ctx->R2Size : 0.f; }
 void* kgmt_stream(const kgmt_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 long long kgmt_launch_count(const kgmt_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+/* bounds-checked build (make check): {first failing site id, failures, offending value, its limit}; resets the record.
+ * Returns KGMT_ERR_STATE from the product build, which compiles the checks away. */
+int kgmt_debug_checks(kgmt_ctx* ctx, int* out4) {
+    if (!ctx || !out4) return KGMT_ERR_INVALID;
+#ifdef KGMT_BOUNDS_CHECK
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpyFromSymbol(out4, g_kgmtCheck, 16));
+    const int z[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyToSymbol(g_kgmtCheck, z, 16));
+    return KGMT_OK;
+#else
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    return fail(ctx, KGMT_ERR_STATE, "this build has no bounds checks (make -C cudasbmp_b200/csrc check)");
+#endif
+}
+
 int kgmt_work_counters(kgmt_ctx* ctx, unsigned long long* out4) {
     if (!ctx || !out4) return KGMT_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));

@@ -14,6 +14,22 @@
 
 namespace kgmt {
 
+/* ------------------------------------------------------------- bounds-checked build --
+ * make -C cudasbmp_b200/csrc check  (-DKGMT_BOUNDS_CHECK -> libkgmt_b200_check.so): every index the kernels form into the
+ * tree, the staging rows, the ballots, the region maps, the cell lists and the exchange slabs is range-checked on the
+ * device; the first failing site and the number of failures are kept in g_kgmtCheck and read with kgmt_debug_checks.
+ * (compute-sanitizer is refused on the GPU pool this was developed on: profiles/r02b_sanitizer_refused.txt.)
+ * The product build compiles the checks away. */
+#ifdef KGMT_BOUNDS_CHECK
+__device__ int g_kgmtCheck[4];            /* [0] first failing site id, [1] failures, [2] offending value, [3] its limit */
+__device__ __forceinline__ void kgmt_check_fail(int site, long long v, long long lim) {
+    if (atomicAdd(&g_kgmtCheck[1], 1) == 0) { g_kgmtCheck[0] = site; g_kgmtCheck[2] = (int)v; g_kgmtCheck[3] = (int)lim; }
+}
+#define KGMT_CHECK_RANGE(site, v, lim) do { if ((long long)(v) < 0 || (long long)(v) >= (long long)(lim)) kgmt_check_fail(site, (long long)(v), (long long)(lim)); } while (0)
+#else
+#define KGMT_CHECK_RANGE(site, v, lim) do { } while (0)
+#endif
+
 /* ------------------------------------------------------------------ Philox4x32-10 --
  * cuRAND's counter-based generator (/usr/local/cuda/include/curand_philox4x32_x.h:88-190),
  * used statelessly: candidate slot s of iteration itr draws its four uniforms
@@ -132,6 +148,7 @@ struct CollideGrid {
     const int* cellStart;      /* [C*C+1] */
     const float4* items;       /* obstacle AABBs, grouped by cell */
     int C; float invX, invY;
+    int nStart = 0, nItems = 0;   /* sizes of the two arrays (bounds-checked build only) */
     struct Cursor { int cx, cy; unsigned pairs; };
     __device__ __forceinline__ int cell(float v, float inv) const {
         return min(max(__float2int_rd(__fmul_rn(v, inv)), 0), C - 1);
@@ -145,12 +162,14 @@ struct CollideGrid {
         bool h = false;
         for (int cy = cy0; cy <= cy1 && !h; ++cy) {
             const int row = cy * C;
+            KGMT_CHECK_RANGE(101, row + cx0, nStart); KGMT_CHECK_RANGE(102, row + cx1 + 1, nStart);
             const int e = cellStart[row + cx1 + 1];
             int k = cellStart[row + cx0];
             /* four items per trip, read unconditionally: an entry past the end of this row's range is another cell's
              * obstacle (or one of the three never-overlapping entries that close the array), and a box that overlaps
              * the step bbox is a collision whichever cell it was filed under — over-reading cannot change the flag */
             for (; k < e && !h; k += 4) {
+                KGMT_CHECK_RANGE(103, k, nItems); KGMT_CHECK_RANGE(104, k + 3, nItems);
                 const float4 o0 = items[k], o1 = items[k + 1], o2 = items[k + 2], o3 = items[k + 3];
                 h = aabb_overlap(bnx, bny, bxx, bxy, o0) | aabb_overlap(bnx, bny, bxx, bxy, o1) |
                     aabb_overlap(bnx, bny, bxx, bxy, o2) | aabb_overlap(bnx, bny, bxx, bxy, o3);

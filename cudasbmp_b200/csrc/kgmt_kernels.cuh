@@ -350,6 +350,7 @@ __device__ __forceinline__ ChunkCand chunk_setup(const KArgs& A, const IterView&
     cc.parent = -1; cc.parentCost = 0.f; cc.valid = false;
     if (cc.live) {
         cc.parent = it.frontierStart + s / it.children;                    /* KGMT.cu:374-376 / :454 */
+        KGMT_CHECK_RANGE(201, cc.parent, it.treeSize);
         cc.x = __ldcg(&A.treeState[cc.parent]);                            /* L2-coherent: written by other SMs */
         cc.parentCost = __ldcg(&A.treeCtrl[cc.parent]).w;
         cc.u = sample_controls((uint32_t)s, it.key0, A.car);
@@ -367,6 +368,8 @@ __device__ __forceinline__ void chunk_finish(const KArgs& A, const IterView& it,
     const Controls u = cc.u;
     int r1 = -1, r2 = -1;
     bool accept = false;
+    KGMT_CHECK_RANGE(202, c, A.chunksCap);
+    if (live) KGMT_CHECK_RANGE(203, s, A.maxCand);
     if (live) {
         r1 = region_r1(x.x, x.y, A.R1Size, A.N);                           /* KGMT.cu:390 */
         r2 = region_r2(x.x, x.y, r1, A.R1Size, A.N, A.R2Size, A.n);        /* KGMT.cu:391 */
@@ -375,6 +378,7 @@ __device__ __forceinline__ void chunk_finish(const KArgs& A, const IterView& it,
         wait_ge(&A.st->scoreReady, it.itr);
         scoresOk = true;
     }
+    if (live) { KGMT_CHECK_RANGE(204, r1 + 1, A.c1 + 1); KGMT_CHECK_RANGE(205, r2 + 1, (long long)A.c1 * A.n * A.n + 1); }
     if (live && r1 >= 0) {          /* maps + accept, KGMT.cu:392-411 on the iteration-start snapshot (App. B #1,#2) */
         if (valid) {
             accept = u.u3 <= __ldcg(&it.score[r1]);
@@ -403,6 +407,7 @@ __device__ __forceinline__ void chunk_finish(const KArgs& A, const IterView& it,
     const unsigned bal = __ballot_sync(0xffffffffu, accept);
     if (accept) {
         const int at = c * CHUNK + __popc(bal & ((1u << lane) - 1u));
+        KGMT_CHECK_RANGE(206, at, A.maxCand);
         const float cost = __fadd_rn(cc.parentCost, u.duration);                   /* :585-586, :631-633 */
         __stcg(&it.stageState[at], x);
         __stcg(&it.stageCtrl[at], make_float4(u.a, u.steering, u.duration, cost));
@@ -456,6 +461,7 @@ struct TileStream {
 
 __device__ __forceinline__ void tile_issue(const TileStream& ts, unsigned g) {
     const int b = (int)(g & 1u);
+    KGMT_CHECK_RANGE(209, (int)(g % (unsigned)ts.T), ts.T);
     mbar_expect_tx(&ts.full[b], STREAM_TILE * 16u);
     bulk_g2s(ts.buf0 + b * STREAM_TILE, ts.obstacles + (size_t)(g % (unsigned)ts.T) * STREAM_TILE, STREAM_TILE * 16u, &ts.full[b]);
 }
@@ -549,6 +555,7 @@ __device__ __forceinline__ void insert_block(const KArgs& A, const IterView& it,
             const float4 x = __ldcg(&it.stageState[ci * CHUNK + r]);
             const float4 u = __ldcg(&it.stageCtrl[ci * CHUNK + r]);
             const int dst = dst0 + q;
+            KGMT_CHECK_RANGE(207, dst, A.maxTree); KGMT_CHECK_RANGE(208, ci * CHUNK + r, A.maxCand);
             A.treeState[dst] = x;
             A.treeCtrl[dst] = u;
             A.treeParent[dst] = it.parentOf ? __ldcg(&it.parentOf[slot]) : it.frontierStart + slot / it.children;
@@ -624,8 +631,8 @@ __device__ __forceinline__ ColSet stage_collision(const KArgs& A, unsigned char*
         __syncthreads();
         if (tid == 0) { tile_issue(ts, 0u); tile_issue(ts, 1u); }
     }
-    cs.gridS = CollideGrid{sCellStart, sItems, A.cullC, A.cullInvX, A.cullInvY};
-    cs.gridG = CollideGrid{A.cellStart, A.cellItems, A.cullC, A.cullInvX, A.cullInvY};
+    cs.gridS = CollideGrid{sCellStart, sItems, A.cullC, A.cullInvX, A.cullInvY, A.cellStartInts, A.numItems};
+    cs.gridG = CollideGrid{A.cellStart, A.cellItems, A.cullC, A.cullInvX, A.cullInvY, A.cellStartInts, A.numItems};
     cs.allS = CollideSmemAll{sObs, A.K};
     cs.allG = CollideSmemAll{A.obstacles, A.K};
     return cs;
@@ -1535,6 +1542,7 @@ __global__ void __launch_bounds__(TILE, 3) expand_sharded_kernel(const KArgs A, 
                     const int row = q0g + q;
                     const int dst = it.treeSize + row;
                     const int parent = it.frontierStart + slot / it.children;
+                    KGMT_CHECK_RANGE(210, dst, A.maxTree); KGMT_CHECK_RANGE(211, parent, it.treeSize);
                     for (int p = 0; p < world; ++p) {
                         P.treeState[p][dst] = x;
                         P.treeCtrl[p][dst] = u;
@@ -1569,6 +1577,7 @@ __global__ void __launch_bounds__(TILE, 3) expand_sharded_kernel(const KArgs A, 
                     if (k == 3) { if (mine[at] != 0) continue; val = (int)stampNew; }
                     else val = mine[at] + sum;
                 }
+                KGMT_CHECK_RANGE(212, at, 7 * c1 + 4 * c2);
                 for (int p = 0; p < world; ++p) {
                     P.mapSlab[p][at] = val;
                     if (at2 != (size_t)-1) P.mapSlab[p][at2] = 1;

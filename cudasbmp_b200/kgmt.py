@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libkgmt_b200.so")
+# KGMT_LIB selects another build of the same ABI (the bounds-checked twin libkgmt_b200_check.so: scripts/bounds_check.sh)
+LIB_PATH = os.environ.get("KGMT_LIB") or os.path.join(HERE, "libkgmt_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM, ERR_COMM = 0, -1, -2, -3, -4, -5
 STOP = {0: "running", 1: "solved", 2: "tree_full", 3: "iter_limit", 4: "frontier_empty", 5: "peer_solved"}
@@ -45,7 +46,7 @@ ABI_SYMBOLS = [
     "kgmt_params_from_yaml", "kgmt_stage_update_maps", "kgmt_stage_insert", "kgmt_work_counters", "kgmt_batch_cluster_size",
     "kgmt_peer_expand_iterations", "kgmt_peer_plan",
     "kgmt_comm_unique_id", "kgmt_comm_init", "kgmt_comm_destroy", "kgmt_comm_barrier", "kgmt_comm_rank", "kgmt_comm_world",
-    "kgmt_plan_batch_sharded", "kgmt_plan_portfolio", "kgmt_expand_sharded", "kgmt_plan_sharded",
+    "kgmt_plan_batch_sharded", "kgmt_plan_portfolio", "kgmt_expand_sharded", "kgmt_plan_sharded", "kgmt_debug_checks",
 ]
 EXCHANGE_FUSED, EXCHANGE_PEER_LAUNCHES, EXCHANGE_NCCL = 0, 1, 2
 
@@ -179,6 +180,7 @@ def load():
                                       C.POINTER(C.c_int)]
     L.kgmt_expand_sharded.argtypes = [vp, C.c_int, C.POINTER(IterStats), f32p]
     L.kgmt_plan_sharded.argtypes = [vp, f32p, f32p, C.POINTER(Result)]
+    L.kgmt_debug_checks.argtypes = [vp, C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -386,6 +388,12 @@ class KGMT:
         out = (C.c_ulonglong * 4)()
         self._ck(load().kgmt_work_counters(self._h, out))
         return {"steps": int(out[0]), "pairs": int(out[1]), "expansions": int(out[2])}
+
+    def debug_checks(self):
+        """Bounds-checked build only: {site, failures, value, limit} of the device-side index checks since the last call."""
+        out = (C.c_int * 4)()
+        self._ck(load().kgmt_debug_checks(self._h, out))
+        return {"site": out[0], "failures": out[1], "value": out[2], "limit": out[3]}
 
     def extract_path(self, node=-1, max_rows=4096):
         buf = np.zeros((max_rows, 7), dtype=np.float32)

@@ -328,6 +328,10 @@ long long kgmt_launch_count(const kgmt_ctx* ctx);                /* kernels of t
  * (collisionCheck.cu:6-14 calls; with the culled back end: entries read from the cell lists, padding included),
  * candidate edges, 0}.  The non-recording kernels do not count (the counters cost instructions). */
 int  kgmt_work_counters(kgmt_ctx* ctx, unsigned long long* out4);
+/* the bounds-checked build of the library (libkgmt_b200_check.so, -DKGMT_BOUNDS_CHECK): out4 = {id of the first index
+ * check that failed on the device (0 = none), number of failures, offending value, its limit} since the last call.
+ * The product build returns KGMT_ERR_STATE. */
+int  kgmt_debug_checks(kgmt_ctx* ctx, int* out4);
 /* diagnostics: enable != 0 turns on per-iteration device timestamps; out8 rows (8 x u64) = {globaltimer ns when the
  * iteration was finalized, candidates << 32 | accepted, then CTA 0's globaltimer at: iteration start, phase A done,
  * first grid barrier passed, phase B done, last grid barrier passed, 0} of the last plan; returns rows written */

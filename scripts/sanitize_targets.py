@@ -1,4 +1,5 @@
-"""Small, complete runs of every kernel family of the library, for compute-sanitizer (scripts/gpu_sanitize.sh):
+"""Small, complete runs of every kernel family of the library, for compute-sanitizer (scripts/gpu_sanitize.sh) and for the
+bounds-checked build (scripts/bounds_check.sh: KGMT_LIB=cudasbmp_b200/libkgmt_b200_check.so):
     python scripts/sanitize_targets.py c1|c2|c3s|batch|peer2|fused1|stage
 Each target ends with a result check, so a sanitizer run that also prints 'target ok' exercised the real path."""
 import os, sys
@@ -78,4 +79,8 @@ elif what == "stage":                  # stage entry points: propagate, update_m
     p.stage_scores()
 else:
     raise SystemExit("unknown target " + what)
+if os.environ.get("KGMT_LIB"):         # the bounds-checked twin of the library: the device-side index checks must all have held
+    chk = p.debug_checks()
+    print("bounds checks:", chk)
+    assert chk["failures"] == 0, chk
 print("target ok:", what)
