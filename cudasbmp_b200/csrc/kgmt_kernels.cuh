@@ -248,6 +248,7 @@ __device__ __forceinline__ int ld_acquire_sys_s32(const int* p) {
     return v;
 }
 __device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 /* wait until *p >= want: relaxed polling with back-off, one acquire fence at the end */
 __device__ __forceinline__ void wait_ge(const int* p, int want) {
     unsigned ns = 64;
@@ -1396,9 +1397,17 @@ __device__ __forceinline__ bool peer_wait_ge(const int* p, int want) {
     }
     return true;
 }
-/* every thread of the CTA waits until the local word has reached `want` (written by CTA 0 with a gpu-scope release) */
+/* every thread of the CTA waits until the local word has reached `want`.  The word is written by CTA 0 / warp 0 with a
+ * gpu-scope release AFTER that warp acquired the peers' words at system scope, so the chain
+ *     peer stores -> peer release.sys -> CTA 0 acquire.sys -> CTA 0 release.gpu -> this acquire.gpu -> CTA barrier
+ * orders the peers' stores before every thread of this CTA (causality is transitive across scopes); peer data is read
+ * with ld.cg, never from L1.  System-scope fences are kept to ONE thread per hand-shake: executed by every thread (or by
+ * one thread of each of 444 CTAs) they cost ~10 us per hand-shake on B200 (profiles/r02d_fused_timeline.txt). */
 __device__ __forceinline__ void cta_wait_flag(const int* p, int want) {
-    if (threadIdx.x == 0) { unsigned ns = 32; while ((int)(ld_acquire_s32(p) - want) < 0) { __nanosleep(ns); if (ns < 512) ns <<= 1; } }
+    if (threadIdx.x == 0) {
+        unsigned ns = 32;
+        while ((int)(ld_acquire_s32(p) - want) < 0) { __nanosleep(ns); if (ns < 256) ns <<= 1; }
+    }
     __syncthreads();
 }
 
@@ -1432,6 +1441,15 @@ __global__ void __launch_bounds__(TILE, 3) expand_sharded_kernel(const KArgs A, 
         if (S.stop != STOP_RUNNING) break;
         const int seq = seq0 + iter + 1;
         IterView it = make_view(A, S);
+        const int logRow = S.iterationsDone;
+        auto stamp = [&](int colIdx) {        /* kgmt_iteration_log: CTA 0's clock at the phase boundaries */
+            if (A.iterLog && cta == 0 && tid == 0 && logRow < 255) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                A.iterLog[8 * logRow + colIdx] = t;
+            }
+        };
+        stamp(2);
         const int numBlocks = (it.numChunks + BLK_CHUNKS - 1) / BLK_CHUNKS;
         const int bBase = numBlocks / world, bRem = numBlocks % world;
         const int bLo = rank * bBase + min(rank, bRem), bHi = bLo + bBase + (rank < bRem ? 1 : 0);
@@ -1464,6 +1482,7 @@ __global__ void __launch_bounds__(TILE, 3) expand_sharded_kernel(const KArgs A, 
                 }
             }
         }
+        stamp(3);
         grid.sync();                                                    /* 1: ballots, block sums, deltas of this rank are final */
 
         /* ---- counts: CTA 0 / warp 0 talks to the peers */
@@ -1473,13 +1492,13 @@ __global__ void __launch_bounds__(TILE, 3) expand_sharded_kernel(const KArgs A, 
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
             if (lane == 0) { plan->goalLocal = ~0ull; plan->goalGlobal = ~0ull; }
-            __threadfence_system();
             bool ok = true;
             int cnt = 0;
             if (lane < world) {
                 PeerMail* m = P.mail[lane] + rank;
                 m->count = mine;
-                __threadfence_system();
+                /* release at system scope: cumulative over everything the grid barrier ordered before this thread —
+                 * every CTA's delta increments of this iteration */
                 st_release_sys_s32(&m->seq1, seq);
                 const PeerMail* in = P.mail[rank] + lane;
                 ok = peer_wait_ge(&in->seq1, seq);
@@ -1496,13 +1515,15 @@ __global__ void __launch_bounds__(TILE, 3) expand_sharded_kernel(const KArgs A, 
             __syncwarp();
             if (lane == 0) st_release_s32(&plan->ready1, seq);
         }
-        cta_wait_flag(&plan->ready1, seq);
+        cta_wait_flag(&plan->ready1, seq);                              /* peers' deltas are read below */
         if (*(volatile const int*)&plan->err) break;
-        __threadfence_system();                                         /* peers' deltas are read below */
+        stamp(4);
         const int base = *(volatile const int*)&plan->base, total = *(volatile const int*)&plan->total;
 
         /* ---- pack: this rank's accepted rows into every replica's tree (updateG on every replica, KGMT.cu:555-591) */
-        for (int blk = bLo + cta; blk < bHi; blk += nCta) {
+        const int packSplit = insert_split(bHi - bLo, nCta);            /* few blocks: several CTAs share one (every n-th group of 32 rows) */
+        for (int v = cta; v < (bHi - bLo) * packSplit; v += nCta) {
+            const int blk = bLo + v / packSplit, slice = v - (v / packSplit) * packSplit;
             int m2 = 0;
             for (int b = bLo + tid; b < blk; b += TILE) m2 += __ldcg(&it.blockSum[b]);
             const int prefix = block_sum(m2, sRed);
@@ -1521,13 +1542,13 @@ __global__ void __launch_bounds__(TILE, 3) expand_sharded_kernel(const KArgs A, 
             const int W = __shfl_sync(0xffffffffu, incl, 31);
             const int c0 = blk * BLK_CHUNKS + warp * 32;
             const int q0g = base + prefix + warpBase;
-            for (int q0 = 0; q0 < W; q0 += 32) {
+            for (int q0 = 32 * slice; q0 < W; q0 += 32 * packSplit) {
                 const int q = q0 + lane;
                 int i = 0;
 #pragma unroll
                 for (int step = 16; step > 0; step >>= 1) {
-                    const int v = __shfl_sync(0xffffffffu, incl, i + step - 1);
-                    if (v <= q) i += step;
+                    const int v2 = __shfl_sync(0xffffffffu, incl, i + step - 1);
+                    if (v2 <= q) i += step;
                 }
                 i = min(i, 31);
                 const unsigned m = __shfl_sync(0xffffffffu, mask, i);
@@ -1555,47 +1576,61 @@ __global__ void __launch_bounds__(TILE, 3) expand_sharded_kernel(const KArgs A, 
             __syncthreads();
         }
 
-        /* ---- reduce: this rank's share of the delta index space, new values into every replica's maps */
+        /* ---- reduce: this rank's share of the delta index space (in 16-byte vectors: c1, c2 and so every section are
+         * multiples of 4 ints or handled by the scalar tail), new values into every replica's maps.  The loads of one
+         * vector from every rank are independent and issued together: over NVLink the pass is latency bound. */
         {
-            const size_t per = deltaInts / world, extra = deltaInts % world;
-            const size_t lo = rank * per + min((size_t)rank, extra), hi = lo + per + ((size_t)rank < extra ? 1 : 0);
+            const size_t nVec = deltaInts / 4;                           /* deltaInts = 4 (c1 + c2) */
+            const size_t perV = nVec / world, extraV = nVec % world;
+            const size_t loV = rank * perV + min((size_t)rank, extraV), hiV = loV + perV + ((size_t)rank < extraV ? 1 : 0);
             const unsigned stampNew = (unsigned)it.itr + 1u;
             const int* mine = P.mapSlab[rank];
-            for (size_t idx = lo + (size_t)cta * TILE + tid; idx < hi; idx += (size_t)nCta * TILE) {
-                int sum = 0;
-                for (int p = 0; p < world; ++p) sum += __ldcg(&P.delta[p][idx]);
-                if (sum == 0) continue;
-                size_t at; int val; size_t at2 = (size_t)-1;
-                if (idx < 4 * c1) {
-                    const size_t k = idx / c1, i = idx - k * c1;
-                    if (k == 3) continue;
-                    at = k * c1 + i; val = mine[at] + sum;
-                    if (k == 1) at2 = 3 * c1 + i;                              /* R1Avail, KGMT.cu:400 */
-                } else {
-                    const size_t j = idx - 4 * c1, k = j / c2, i = j - k * c2;
-                    at = 7 * c1 + k * c2 + i;
-                    if (k == 3) { if (mine[at] != 0) continue; val = (int)stampNew; }
-                    else val = mine[at] + sum;
-                }
-                KGMT_CHECK_RANGE(212, at, 7 * c1 + 4 * c2);
+            for (size_t vIdx = loV + (size_t)cta * TILE + tid; vIdx < hiV; vIdx += (size_t)nCta * TILE) {
+                int4 acc = make_int4(0, 0, 0, 0);
+#pragma unroll 4
                 for (int p = 0; p < world; ++p) {
-                    P.mapSlab[p][at] = val;
-                    if (at2 != (size_t)-1) P.mapSlab[p][at2] = 1;
+                    const int4 d = __ldcg(reinterpret_cast<const int4*>(P.delta[p]) + vIdx);
+                    acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+                }
+                if ((acc.x | acc.y | acc.z | acc.w) == 0) continue;
+                const int sums[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int sum = sums[e];
+                    if (sum == 0) continue;
+                    const size_t idx = vIdx * 4 + e;
+                    size_t at; int val; size_t at2 = (size_t)-1;
+                    if (idx < 4 * c1) {
+                        const size_t k = idx / c1, i = idx - k * c1;
+                        if (k == 3) continue;
+                        at = k * c1 + i; val = __ldcg(&mine[at]) + sum;
+                        if (k == 1) at2 = 3 * c1 + i;                          /* R1Avail, KGMT.cu:400 */
+                    } else {
+                        const size_t j = idx - 4 * c1, k = j / c2, i = j - k * c2;
+                        at = 7 * c1 + k * c2 + i;
+                        if (k == 3) { if (__ldcg(&mine[at]) != 0) continue; val = (int)stampNew; }
+                        else val = __ldcg(&mine[at]) + sum;
+                    }
+                    KGMT_CHECK_RANGE(212, at, 7 * c1 + 4 * c2);
+                    for (int p = 0; p < world; ++p) {
+                        P.mapSlab[p][at] = val;
+                        if (at2 != (size_t)-1) P.mapSlab[p][at2] = 1;
+                    }
                 }
             }
         }
-        __threadfence_system();
+        stamp(5);
         grid.sync();                                                    /* 2: every pack / reduce store of this rank is issued */
 
         /* ---- goal exchange = the barrier across the GPUs */
         if (cta == 0 && warp == 0) {
-            __threadfence_system();
             bool ok = true;
             unsigned long long g = ~0ull;
             if (lane < world) {
                 PeerMail* m = P.mail[lane] + rank;
                 m->goal = *(volatile unsigned long long*)&plan->goalLocal;
-                __threadfence_system();
+                /* system-scope release, cumulative over the grid barrier: every row and map value this rank stored into
+                 * the peers' memory is visible to a peer that acquires this word */
                 st_release_sys_s32(&m->seq2, seq);
                 const PeerMail* in = P.mail[rank] + lane;
                 ok = peer_wait_ge(&in->seq2, seq);
@@ -1609,9 +1644,9 @@ __global__ void __launch_bounds__(TILE, 3) expand_sharded_kernel(const KArgs A, 
             __syncwarp();
             if (lane == 0) st_release_s32(&plan->ready2, seq);
         }
-        cta_wait_flag(&plan->ready2, seq);
+        cta_wait_flag(&plan->ready2, seq);                              /* rows and map values written by the peers are read from here on */
         if (*(volatile const int*)&plan->err) break;
-        __threadfence_system();                                         /* rows and map values written by the peers are read from here on */
+        stamp(6);
 
         /* ---- finish: zero the delta slab, recount R1Cov, advance the planner scalars */
         {
@@ -1644,7 +1679,14 @@ __global__ void __launch_bounds__(TILE, 3) expand_sharded_kernel(const KArgs A, 
         if (cta == 0 && tid < COPIED_WORDS && tid != THRESHOLD_WORD)
             reinterpret_cast<int*>(st)[tid] = reinterpret_cast<const int*>(&S)[tid];
         __threadfence();
+        if (cta == 0 && tid == 0 && A.iterLog && logRow < 255) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            A.iterLog[8 * logRow] = t;
+            A.iterLog[8 * logRow + 1] = ((unsigned long long)(unsigned)it.M << 32) | (unsigned)total;
+        }
         grid.sync();                                                    /* 3: delta zeroed, R1Cov recounted */
+        stamp(7);
         if (cta == nCta - 1 && S.stop == STOP_RUNNING) {
             scores_block(A, sP, A.R1Score[S.itr & 1]);
             __threadfence();
@@ -1695,10 +1737,10 @@ __global__ void __launch_bounds__(TILE) propagate_only_kernel(const KArgs A, con
         const Controls u = sample_controls(slot0 + (uint32_t)s, key0, A.car);
         bool valid;
         if (COL == COL_GRID_SMEM) {
-            const CollideGrid col{sCellStart, sItems, A.cullC, A.cullInvX, A.cullInvY};
+            const CollideGrid col{sCellStart, sItems, A.cullC, A.cullInvX, A.cullInvY, A.cellStartInts, A.numItems};
             valid = propagate_edge(x, u, dyn, col);
         } else if (COL == COL_GRID_GLOBAL) {
-            const CollideGrid col{A.cellStart, A.cellItems, A.cullC, A.cullInvX, A.cullInvY};
+            const CollideGrid col{A.cellStart, A.cellItems, A.cullC, A.cullInvX, A.cullInvY, A.cellStartInts, A.numItems};
             valid = propagate_edge(x, u, dyn, col);
         } else if (COL == COL_BRUTE_SMEM) {
             const CollideSmemAll col{sObs, A.K};
