@@ -606,7 +606,8 @@ int kgmt_create(const kgmt_params* p, kgmt_ctx** out) {
     CU(cudaMalloc(&ctx->treeParent, T * 4));
     const size_t c1 = (size_t)ctx->c1, c2 = ctx->c2;
     ctx->mapSlabInts = 7 * c1 + 4 * c2;
-    ctx->chunksCap = ((size_t)ctx->maxCand + CHUNK - 1) / CHUNK + 1;
+    /* whole scan blocks: staged_parent reads the 256 ballots of a block with 128-bit loads */
+    ctx->chunksCap = ((((size_t)ctx->maxCand + CHUNK - 1) / CHUNK + 1) + BLK_CHUNKS - 1) / BLK_CHUNKS * BLK_CHUNKS;
     ctx->blocksCap = (ctx->chunksCap + BLK_CHUNKS - 1) / BLK_CHUNKS + 1;
     /* one slab: region maps, then the per-iteration scan block sums — a re-plan clears all of it with ONE memset */
     const size_t bookInts = 3 * ctx->blocksCap;

@@ -84,24 +84,35 @@ __device__ __forceinline__ Controls sample_controls(uint32_t slot, uint32_t key0
 /* --------------------------------------------------------------------- region index --
  * getR1 / getR2, src/planners/KGMT.cu:602-629 (== OccupancyGrid::getCellIndex,
  * src/occupancyMaps/OccupancyGrid.cu:12-19): IEEE division, truncation toward zero. */
-__device__ __forceinline__ int region_r1(float x, float y, float R1Size, int N) {
+struct RegionCell { int r1, cx, cy; };     /* R1 index (-1 = outside) and its column / row */
+__device__ __forceinline__ RegionCell region_r1_cell(float x, float y, float R1Size, int N) {
     const int cx = __float2int_rz(__fdiv_rn(x, R1Size));
     const int cy = __float2int_rz(__fdiv_rn(y, R1Size));
-    return (cx >= 0 && cx < N && cy >= 0 && cy < N) ? cy * N + cx : -1;
+    return RegionCell{(cx >= 0 && cx < N && cy >= 0 && cy < N) ? cy * N + cx : -1, cx, cy};
+}
+__device__ __forceinline__ int region_r1(float x, float y, float R1Size, int N) { return region_r1_cell(x, y, R1Size, N).r1; }
+/* getR2 with the R1 column / row already known (r1 = cy * N + cx, so r1 / N and r1 % N are cy and cx) */
+__device__ __forceinline__ int region_r2_cell(float x, float y, const RegionCell c, float R1Size, float R2Size, int n) {
+    if (c.r1 < 0) return -1;
+    const float lx = __fmaf_rn(-(float)c.cx, R1Size, x);      /* x - cx*R1Size, one FFMA as the reference's SASS */
+    const float ly = __fmaf_rn(-(float)c.cy, R1Size, y);
+    const int cx = __float2int_rz(__fdiv_rn(lx, R2Size));
+    const int cy = __float2int_rz(__fdiv_rn(ly, R2Size));
+    return (cx >= 0 && cx < n && cy >= 0 && cy < n) ? c.r1 * (n * n) + cy * n + cx : -1;
 }
 __device__ __forceinline__ int region_r2(float x, float y, int r1, float R1Size, int N, float R2Size, int n) {
     if (r1 < 0) return -1;
-    const int cyR1 = r1 / N, cxR1 = r1 - cyR1 * N;
-    const float lx = __fmaf_rn(-(float)cxR1, R1Size, x);      /* x - cx*R1Size, one FFMA as the reference's SASS */
-    const float ly = __fmaf_rn(-(float)cyR1, R1Size, y);
-    const int cx = __float2int_rz(__fdiv_rn(lx, R2Size));
-    const int cy = __float2int_rz(__fdiv_rn(ly, R2Size));
-    return (cx >= 0 && cx < n && cy >= 0 && cy < n) ? r1 * (n * n) + cy * n + cx : -1;
+    const int cyR1 = r1 / N;
+    return region_r2_cell(x, y, RegionCell{r1, r1 - cyR1 * N, cyR1}, R1Size, R2Size, n);
 }
 
-/* goal test, KGMT.cu:635-638: differences in float, squares/sqrt in double, '<' on the narrowed float */
+/* goal test, KGMT.cu:635-638: differences in float, squares/sqrt in double, '<' on the narrowed float.
+ * The first line only skips work: dx*dx is exact in double and every later operation (+, sqrt, narrowing) is correctly
+ * rounded, hence monotone, so dist >= |dx| and dist >= |dy| as floats — a difference of r or more decides 'false'. */
 __device__ __forceinline__ bool in_goal(float x, float y, float gx, float gy, float r) {
-    const double dx = (double)__fsub_rn(x, gx), dy = (double)__fsub_rn(y, gy);
+    const float fx = __fsub_rn(x, gx), fy = __fsub_rn(y, gy);
+    if (!(fabsf(fx) < r) || !(fabsf(fy) < r)) return false;
+    const double dx = (double)fx, dy = (double)fy;
     const float dist = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
     return dist < r;
 }

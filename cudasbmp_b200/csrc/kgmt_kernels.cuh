@@ -71,18 +71,20 @@ struct DevState {
      * lagging CTA see an i+1 goal, stop alone and hang the rest at the next barrier.  A slot written in iteration i is
      * next written in i+2, which no CTA enters before all have passed barrier i+1, i.e. after all have read slot i & 1.
      * A goal stops the plan, so a slot never needs clearing inside a plan. */
-    unsigned long long goalBest[2];                             /* (cost bits << 32) | candidate slot, ~0 = none (atomicMin) */
+    /* each group of live words has its own 128-byte line: thousands of warps poll insertDone / scoreReady while CTA 0
+     * rewrites the copied words and thread 0 of every CTA reads goalBest right after the barrier */
+    alignas(128) unsigned long long goalBest[2];                /* (cost bits << 32) | candidate slot, ~0 = none (atomicMin) */
     int goalIdx;                                                /* tree index of the goal node (written by its inserter) */
-    int scoreReady;                                             /* scores of this iteration are complete (release/acquire) */
-    int insertDone;                                             /* scan blocks inserted so far, whole plan (release counter) */
     int peerSolved[2];                                          /* portfolio race: a peer's win as seen before this iteration's barrier */
     int pad2;
     /* work counters (diagnostics, kgmt_work_counters): Euler steps executed, (step, obstacle) AABB tests executed */
     unsigned long long stepsDone, pairsTested;
+    alignas(128) int scoreReady;                                /* scores of this iteration are complete (release/acquire) */
+    alignas(128) int insertDone;                                /* scan blocks inserted so far, whole plan (release counter) */
 };
 constexpr int COPIED_WORDS = 24;
 constexpr int THRESHOLD_WORD = 7;         /* R1Threshold: written by scores_block straight to global memory, never copied back */
-static_assert(offsetof(DevState, goalBest) == COPIED_WORDS * 4, "DevState layout");
+static_assert(offsetof(DevState, goalBest) == 128 && COPIED_WORDS * 4 <= 128, "DevState layout");
 static_assert(offsetof(DevState, R1Threshold) == THRESHOLD_WORD * 4, "DevState layout");
 
 struct KArgs {
@@ -269,6 +271,19 @@ __device__ __forceinline__ int block_sum(int v, int* sRed /* [WARPS] */) {
     return t;
 }
 
+/* two sums at once (same barriers as one) */
+__device__ __forceinline__ int2 block_sum2(int a, int b, int* sRed /* [2 * WARPS] */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { sRed[threadIdx.x >> 5] = a; sRed[WARPS + (threadIdx.x >> 5)] = b; }
+    __syncthreads();
+    int ta = 0, tb = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) { ta += sRed[w]; tb += sRed[WARPS + w]; }
+    return make_int2(ta, tb);
+}
+
 /* Ordered insertion of one scan block can be SPLIT over several CTAs (each takes every n-th group of 32 rows): small
  * iterations have one or two blocks with thousands of accepted rows, and one CTA moving them is a chain of dependent L2
  * round trips (4-10 us of a 20 us iteration on config 1).  Pure function of the iteration shape, so every CTA agrees. */
@@ -341,8 +356,56 @@ struct ChunkCand {
     float4 x; Controls u; int parent; float parentCost; bool live, valid;
 };
 
+/* ------------------------------------------------ parents straight from the staging rows ---
+ * Phase B moves the accepted rows of iteration i from the staging buffers into the tree, and phase A of iteration i+1
+ * reads its parents from the tree: a chunk that starts right after the barrier would wait for the whole of phase B
+ * (block sums -> ballots -> rows -> fence -> flag -> poll: 4-5 us of dependent L2 round trips, every iteration).
+ * Until the tree rows are announced a chunk whose 32 candidates share ONE parent (32 children per node, the reference
+ * policy while the tree has room) fetches that parent from where phase A left it: the q-th new node is the r-th
+ * accepted candidate of the scan block whose prefix range holds q; the block comes from the per-CTA prefix of the
+ * block sums (already loaded for advance_state), the chunk and the rank inside it from the block's 256 ballots
+ * (eight per lane, one warp scan).  Same row as the tree will hold, so the same bits. */
+constexpr int BLK_PRE_CAP = TILE;         /* scan blocks whose prefix a CTA keeps (one per thread) */
+struct StagedParents {
+    const int* blkPre;                    /* shared memory: exclusive prefix of the previous iteration's block sums */
+    int numBlocks, numChunks;             /* of the previous iteration */
+    const unsigned* mask; const float4* stageState; const float4* stageCtrl;
+};
+__device__ __forceinline__ void staged_parent(const StagedParents& sp, int q, int lane, float4& x, float& cost) {
+    int lo = 0, hi = sp.numBlocks - 1;
+    while (lo < hi) {                     /* last block whose prefix is <= q (empty blocks share a prefix with their successor) */
+        const int mid = (lo + hi + 1) >> 1;
+        if (sp.blkPre[mid] <= q) lo = mid; else hi = mid - 1;
+    }
+    const int r = q - sp.blkPre[lo];      /* rank of the row inside the block */
+    const int c0 = lo * BLK_CHUNKS + lane * 8;
+    const uint4* mp = reinterpret_cast<const uint4*>(sp.mask + c0);
+    const uint4 ma = __ldcg(mp), mb = __ldcg(mp + 1);
+    unsigned m[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};      /* fully unrolled below: stays in registers */
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { if (c0 + k >= sp.numChunks) m[k] = 0u; cnt += __popc(m[k]); }   /* ballots past the end are stale */
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const unsigned owners = __ballot_sync(0xffffffffu, incl > r);
+    const int owner = owners ? (__ffs(owners) - 1) : 31;
+    /* every lane resolves (chunk, rank) as if it were the owner; the owner's answer is broadcast */
+    int rr = r - (incl - cnt), ci = c0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { const int pc = __popc(m[k]); if (ci == c0 + k && rr >= pc) { rr -= pc; ci = c0 + k + 1; } }
+    ci = __shfl_sync(0xffffffffu, ci, owner);
+    rr = __shfl_sync(0xffffffffu, rr, owner);
+    KGMT_CHECK_RANGE(210, ci, sp.numChunks); KGMT_CHECK_RANGE(211, rr, CHUNK);
+    x = __ldcg(&sp.stageState[ci * CHUNK + rr]);
+    cost = __ldcg(&sp.stageCtrl[ci * CHUNK + rr]).w;
+}
+
 /* stage 2 + the parent read of stage 3 for lane `lane` of chunk c */
-__device__ __forceinline__ ChunkCand chunk_setup(const KArgs& A, const IterView& it, int c, int lane) {
+__device__ __forceinline__ ChunkCand chunk_setup(const KArgs& A, const IterView& it, int c, int lane,
+                                                 bool staged = false, const StagedParents& sp = StagedParents{}) {
+    float4 sx = make_float4(0.f, 0.f, 0.f, 0.f); float sc = 0.f;
+    if (staged) staged_parent(sp, c, lane, sx, sc);               /* whole warp: one parent (children == 32) */
     ChunkCand cc;
     const int s = c * CHUNK + lane;
     cc.live = s < it.M;
@@ -350,10 +413,13 @@ __device__ __forceinline__ ChunkCand chunk_setup(const KArgs& A, const IterView&
     cc.u = Controls{0.f, 0.f, 0.f, 0.f};
     cc.parent = -1; cc.parentCost = 0.f; cc.valid = false;
     if (cc.live) {
-        cc.parent = it.frontierStart + s / it.children;                    /* KGMT.cu:374-376 / :454 */
+        cc.parent = it.frontierStart + (it.children == 32 ? (s >> 5) : s / it.children);   /* KGMT.cu:374-376 / :454 */
         KGMT_CHECK_RANGE(201, cc.parent, it.treeSize);
-        cc.x = __ldcg(&A.treeState[cc.parent]);                            /* L2-coherent: written by other SMs */
-        cc.parentCost = __ldcg(&A.treeCtrl[cc.parent]).w;
+        if (staged) { cc.x = sx; cc.parentCost = sc; }
+        else {
+            cc.x = __ldcg(&A.treeState[cc.parent]);                        /* L2-coherent: written by other SMs */
+            cc.parentCost = __ldcg(&A.treeCtrl[cc.parent]).w;
+        }
         cc.u = sample_controls((uint32_t)s, it.key0, A.car);
     }
     return cc;
@@ -372,8 +438,9 @@ __device__ __forceinline__ void chunk_finish(const KArgs& A, const IterView& it,
     KGMT_CHECK_RANGE(202, c, A.chunksCap);
     if (live) KGMT_CHECK_RANGE(203, s, A.maxCand);
     if (live) {
-        r1 = region_r1(x.x, x.y, A.R1Size, A.N);                           /* KGMT.cu:390 */
-        r2 = region_r2(x.x, x.y, r1, A.R1Size, A.N, A.R2Size, A.n);        /* KGMT.cu:391 */
+        const RegionCell rc = region_r1_cell(x.x, x.y, A.R1Size, A.N);     /* KGMT.cu:390 */
+        r1 = rc.r1;
+        r2 = region_r2_cell(x.x, x.y, rc, A.R1Size, A.R2Size, A.n);        /* KGMT.cu:391 */
     }
     if (!scoresOk) {                /* scores of this iteration (and hence the maps of the previous one) are final */
         wait_ge(&A.st->scoreReady, it.itr);
@@ -433,8 +500,9 @@ __device__ __forceinline__ void chunk_finish(const KArgs& A, const IterView& it,
  * scoresOk (warp-uniform) remembers that this iteration's score buffer has been seen complete. */
 template <class Collide, bool RECORD, bool SHARD = false>
 __device__ __forceinline__ void expand_chunk(const KArgs& A, const IterView& it, const DynParams& dyn,
-                                             const Collide& col, int c, int lane, int* hV, int* hI, bool& scoresOk) {
-    ChunkCand cc = chunk_setup(A, it, c, lane);
+                                             const Collide& col, int c, int lane, int* hV, int* hI, bool& scoresOk,
+                                             bool staged = false, const StagedParents& sp = StagedParents{}) {
+    ChunkCand cc = chunk_setup(A, it, c, lane, staged, sp);
     if (RECORD) {                   /* the recording kernels also count the work (kgmt_work_counters) */
         EdgeWork wk{0u, 0u};
         if (cc.live) cc.valid = propagate_edge(cc.x, cc.u, dyn, col, &wk);
@@ -520,10 +588,10 @@ __device__ __forceinline__ int nth_set_bit(unsigned m, int r) {
  * the chunk found by a 5-step shuffle search over the inclusive counts.
  * base = accepted candidates in all earlier blocks. */
 __device__ __forceinline__ void insert_block(const KArgs& A, const IterView& it, int blk, int base, int* sScan /* [WARPS] */,
-                                             int slice = 0, int nslices = 1) {
+                                             int slice = 0, int nslices = 1, bool haveMask = false, unsigned mask0 = 0u) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blk * BLK_CHUNKS + tid;
-    const unsigned mask = (c < it.numChunks) ? __ldcg(&it.chunkMask[c]) : 0u;
+    const unsigned mask = haveMask ? mask0 : ((c < it.numChunks) ? __ldcg(&it.chunkMask[c]) : 0u);
     const int cnt = __popc(mask);
     int incl = cnt;
 #pragma unroll
@@ -647,8 +715,9 @@ __device__ __forceinline__ void stream_drain(const TileStream& ts) {
 
 template <int COL, bool RECORD, class Group>
 __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
-    __shared__ int sRed[WARPS];
+    __shared__ int sRed[2 * WARPS];
     __shared__ float sP[1024];
+    __shared__ int sBlkPre[BLK_PRE_CAP + 1];
     __shared__ DevState S;
     __shared__ int sAccepted;
     __shared__ unsigned long long sGoalBest;
@@ -669,6 +738,11 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
     const int gw = grp.rank * WARPS + warp;
     const int scoreRank = grp.size - 1;
     const int resetRank = grp.size > 1 ? grp.size - 2 : 0;
+    /* insertion items go to the CTAs from the top of the group down (below the two housekeeping CTAs): the first chunks of
+     * an iteration belong to the low ranks, which start them at once from the staging rows */
+    const int insertFirst = (3 * grp.size - 3 - grp.rank) % grp.size;
+    StagedParents prev{sBlkPre, 0, 0, nullptr, nullptr, nullptr};
+    bool prevOk = false;                   /* sBlkPre / prev describe the iteration before the one about to run */
 
     for (int iter = 0; iter < maxIters; ++iter) {
         if (S.stop != STOP_RUNNING) break;
@@ -705,14 +779,24 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
             unsigned* ticket = A.ticket + (it.itr % 3);
             int c = gw;
             int t = 0;
-            /* parents were inserted by the previous phase B, possibly still running on other CTAs */
-            if (c < it.numChunks) wait_ge(&st->insertDone, S.blocksTotal);
+            /* parents were inserted by the previous phase B, possibly still running on other CTAs: until its last block is
+             * announced, take the parent from the staging rows (staged_parent) when the chunk has a single one */
+            bool inserted = false;
+            const bool canStage = prevOk && it.children == CHUNK;
             while (c < it.numChunks) {
                 if (lane == 0) t = (int)atomicAdd(ticket, 1u);
-                if (COL == COL_GRID_SMEM)        expand_chunk<CollideGrid, RECORD>(A, it, dyn, colGridS, c, lane, hV, hI, scoresOk);
-                else if (COL == COL_GRID_GLOBAL) expand_chunk<CollideGrid, RECORD>(A, it, dyn, colGridG, c, lane, hV, hI, scoresOk);
-                else if (COL == COL_BRUTE_SMEM)  expand_chunk<CollideSmemAll, RECORD>(A, it, dyn, colAllS, c, lane, hV, hI, scoresOk);
-                else if (COL == COL_BRUTE_GLOBAL) expand_chunk<CollideSmemAll, RECORD>(A, it, dyn, colAllG, c, lane, hV, hI, scoresOk);
+                bool staged = false;
+                if (!inserted) {
+                    int done = (lane == 0) ? ld_relaxed_s32(&st->insertDone) : 0;       /* one lane reads, all agree */
+                    done = __shfl_sync(0xffffffffu, done, 0);
+                    if (done >= S.blocksTotal) { fence_acq_rel(); inserted = true; }
+                    else if (canStage) staged = true;
+                    else { wait_ge(&st->insertDone, S.blocksTotal); inserted = true; }
+                }
+                if (COL == COL_GRID_SMEM)        expand_chunk<CollideGrid, RECORD>(A, it, dyn, colGridS, c, lane, hV, hI, scoresOk, staged, prev);
+                else if (COL == COL_GRID_GLOBAL) expand_chunk<CollideGrid, RECORD>(A, it, dyn, colGridG, c, lane, hV, hI, scoresOk, staged, prev);
+                else if (COL == COL_BRUTE_SMEM)  expand_chunk<CollideSmemAll, RECORD>(A, it, dyn, colAllS, c, lane, hV, hI, scoresOk, staged, prev);
+                else if (COL == COL_BRUTE_GLOBAL) expand_chunk<CollideSmemAll, RECORD>(A, it, dyn, colAllG, c, lane, hV, hI, scoresOk, staged, prev);
                 c = __shfl_sync(0xffffffffu, t, 0);
             }
         }
@@ -735,12 +819,52 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
         grp.sync();                    /* the one barrier: all ballots, block sums, maps and the goal minimum are final */
         stamp(4);
 
-        /* ---- every CTA advances the planner scalars on its own copy */
+        /* ---- every CTA advances the planner scalars on its own copy.  The same pass over the block sums leaves their
+         * exclusive prefix in shared memory — the insertion base of this CTA's items and the key of staged_parent in the
+         * next phase A — and the ballots of this CTA's first insertion item are fetched alongside: one L2 round trip
+         * after the barrier instead of three (the items and the split depend only on the iteration's shape). */
         const int numBlocks = (it.numChunks + BLK_CHUNKS - 1) / BLK_CHUNKS;
+        const int split = insert_split(numBlocks, A.totalWarps / WARPS);
+        const int blk0 = (insertFirst < numBlocks * split) ? insertFirst / split : -1;
+        const bool preOk = numBlocks <= BLK_PRE_CAP;
+        unsigned mask0 = 0u;
+        int base0 = 0;
         {
-            int mine = 0;
-            for (int b = tid; b < numBlocks; b += TILE) mine += __ldcg(&it.blockSum[b]);
-            const int accepted = block_sum(mine, sRed);
+            if (blk0 >= 0) {
+                const int c0 = blk0 * BLK_CHUNKS + tid;
+                if (c0 < it.numChunks) mask0 = __ldcg(&it.chunkMask[c0]);
+            }
+            int accepted;
+            if (preOk) {
+                const int v = (tid < numBlocks) ? __ldcg(&it.blockSum[tid]) : 0;
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+                __syncthreads();               /* readers of sRed / sBlkPre from the previous round are done */
+                if (lane == 31) sRed[warp] = incl;
+                __syncthreads();
+                int wb = 0, tot = 0;
+#pragma unroll
+                for (int w2 = 0; w2 < WARPS; ++w2) { const int x = sRed[w2]; if (w2 < warp) wb += x; tot += x; }
+                sBlkPre[tid] = wb + incl - v;
+                if (tid == 0) sBlkPre[BLK_PRE_CAP] = tot;
+                accepted = tot;
+                __syncthreads();
+                if (blk0 >= 0) base0 = sBlkPre[blk0];
+            } else {
+                int mine = 0, mineBase = 0;
+                for (int b = tid; b < numBlocks; b += TILE) {
+                    const int v = __ldcg(&it.blockSum[b]);
+                    mine += v;
+                    if (b < blk0) mineBase += v;
+                }
+                const int2 sums = block_sum2(mine, mineBase, sRed);
+                accepted = sums.x;
+                base0 = sums.y;
+            }
+            prev.numBlocks = numBlocks; prev.numChunks = it.numChunks;
+            prev.mask = it.chunkMask; prev.stageState = it.stageState; prev.stageCtrl = it.stageCtrl;
+            prevOk = preOk;
             if (tid == 0) {
                 sGoalBest = *(volatile unsigned long long*)&st->goalBest[it.itr & 1];
                 const bool hadGoal = S.costToGoal != 0.0f;
@@ -779,14 +903,21 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
         if (grp.rank == 0 && tid < COPIED_WORDS && tid != THRESHOLD_WORD)   /* for the host and for the next launch */
             reinterpret_cast<int*>(st)[tid] = reinterpret_cast<const int*>(&S)[tid];
 
-        /* ---- phase B: ordered insertion, scan blocks strided over the CTAs */
-        const int split = insert_split(numBlocks, A.totalWarps / WARPS);
-        for (int v = grp.rank; v < numBlocks * split; v += grp.size) {
+        /* ---- phase B: ordered insertion, scan-block slices strided over the CTAs (first item: base and ballots already here) */
+        for (int v = insertFirst; v < numBlocks * split; v += grp.size) {
             const int blk = v / split;
-            int mine = 0;
-            for (int b = tid; b < blk; b += TILE) mine += __ldcg(&it.blockSum[b]);
-            const int base = block_sum(mine, sRed);
-            insert_block(A, it, blk, base, sRed, v - blk * split, split);
+            if (v == insertFirst) {
+                insert_block(A, it, blk, base0, sRed, v - blk * split, split, true, mask0);
+            } else {
+                int base;
+                if (preOk) base = sBlkPre[blk];
+                else {
+                    int mine = 0;
+                    for (int b = tid; b < blk; b += TILE) mine += __ldcg(&it.blockSum[b]);
+                    base = block_sum(mine, sRed);
+                }
+                insert_block(A, it, blk, base, sRed, v - blk * split, split);
+            }
         }
         stamp(5);
     }
