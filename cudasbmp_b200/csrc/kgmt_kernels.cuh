@@ -435,6 +435,7 @@ __device__ __forceinline__ void chunk_finish(const KArgs& A, const IterView& it,
     const Controls u = cc.u;
     int r1 = -1, r2 = -1;
     bool accept = false;
+    unsigned casOld = 1u; bool casDone = false;        /* first-reached R2 cell: the CAS round trip overlaps the rest of the stage */
     KGMT_CHECK_RANGE(202, c, A.chunksCap);
     if (live) KGMT_CHECK_RANGE(203, s, A.maxCand);
     if (live) {
@@ -455,7 +456,7 @@ __device__ __forceinline__ void chunk_finish(const KArgs& A, const IterView& it,
                 if (stamp == 0u || stamp > (unsigned)it.itr) accept = true;        /* unavailable at iteration start */
                 if (stamp == 0u) {
                     if (SHARD) A.R2StampDelta[r2] = 1;      /* the stamp itself is set at commit, after the all-reduce */
-                    else if (atomicCAS(&A.R2Stamp[r2], 0u, (unsigned)it.itr + 1u) == 0u) atomicAdd(&A.R1Cov[r1], 1);
+                    else { casOld = atomicCAS(&A.R2Stamp[r2], 0u, (unsigned)it.itr + 1u); casDone = true; }   /* answer used last */
                 }
                 atomicAdd(&A.R2Valid[r2], 1);
             }
@@ -486,6 +487,7 @@ __device__ __forceinline__ void chunk_finish(const KArgs& A, const IterView& it,
         __stcg(&it.chunkMask[c], bal);
         if (bal) atomicAdd(&it.blockSum[c / BLK_CHUNKS], __popc(bal));
     }
+    if (casDone && casOld == 0u) atomicAdd(&A.R1Cov[r1], 1);     /* this candidate stamped the cell: covR of updateR1 (KGMT.cu:510-514) */
     if (RECORD && live) {
         A.candState[s] = x;
         A.candCtrl[s] = make_float4(u.a, u.steering, u.duration, u.u3);
@@ -834,6 +836,11 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
                 const int c0 = blk0 * BLK_CHUNKS + tid;
                 if (c0 < it.numChunks) mask0 = __ldcg(&it.chunkMask[c0]);
             }
+            unsigned long long gbNow = ~0ull; int peerNow = 0;     /* thread 0: in flight with the block sums */
+            if (tid == 0) {
+                gbNow = *(volatile unsigned long long*)&st->goalBest[it.itr & 1];
+                if (A.raceId > 0) peerNow = *(volatile int*)&st->peerSolved[it.itr & 1];
+            }
             int accepted;
             if (preOk) {
                 const int v = (tid < numBlocks) ? __ldcg(&it.blockSum[tid]) : 0;
@@ -866,9 +873,9 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
             prev.mask = it.chunkMask; prev.stageState = it.stageState; prev.stageCtrl = it.stageCtrl;
             prevOk = preOk;
             if (tid == 0) {
-                sGoalBest = *(volatile unsigned long long*)&st->goalBest[it.itr & 1];
+                sGoalBest = gbNow;
                 const bool hadGoal = S.costToGoal != 0.0f;
-                advance_state(A, S, accepted, sGoalBest, A.raceId > 0 ? *(volatile int*)&st->peerSolved[it.itr & 1] : 0);
+                advance_state(A, S, accepted, sGoalBest, peerNow);
                 sAccepted = (!hadGoal && S.costToGoal != 0.0f) ? S.goalSlot : -1;
                 if (A.raceId > 0 && grp.rank == 0 && S.stop == STOP_SOLVED) {
                     /* first solution: tell every other GPU of the race (system-scope release over NVLink) */
