@@ -47,6 +47,7 @@ sys.path.insert(0, ROOT)
 METRIC = "checked edge expansions/sec"
 UNIT = "expansions/s"
 B_EXP, B_INS = 33.5, 77.0          # algorithmic HBM bytes per expansion / per accepted node
+STATE_BYTES = 512                  # sizeof(kgmt::DevState): the planner's scalar block read back after every plan
 PLANS_PER_STEP = 64                # a step = one batch of this many complete plans (>= 1 s timed at the driver's 20 steps)
 SAMPLE = os.path.join(ROOT, "bench_data", "c2_frontier_sample.npz")
 
@@ -298,9 +299,33 @@ def ttfs_multi(k, w, local, rank, world, dist, torch, races=101):
             out[name] = {"races": races, "solved": len(solved), "median_ms": statistics.median(tt), "p95_ms": tt[int(0.95 * (len(tt) - 1))],
                          "winner_device_ms_median": statistics.median(x[2] for x in solved),
                          "path_nodes_median": statistics.median(x[3] for x in solved)}
+        # the race alone (kgmt_peer_race, no result exchange): when does the FIRST rank hold a solution?  All ranks are
+        # processes of one host, so time.perf_counter (CLOCK_MONOTONIC) is one clock: first = min over the solving ranks
+        # of their return time - the latest barrier exit.
+        firsts = []
+        for q in range(races + 3):
+            race_id += 1
+            p.set_seed(1000 * q + 1 + rank)
+            p.comm_barrier()
+            t0 = time.perf_counter()
+            r = p.peer_race(init, goal, race_id)
+            t1 = time.perf_counter()
+            row = torch.tensor([t0, t1 if r["stop"] == 1 else float("inf")], dtype=torch.float64, device="cuda")
+            allr = [torch.zeros_like(row) for _ in range(world)]
+            dist.all_gather(allr, row)
+            start = max(float(a[0]) for a in allr)
+            done = min(float(a[1]) for a in allr)
+            if q >= 3 and done != float("inf"):
+                firsts.append((done - start) * 1e3)
+        if firsts and name in out:
+            fs = sorted(firsts)
+            out[name]["first_solution_median_ms"] = statistics.median(fs)
+            out[name]["first_solution_p95_ms"] = fs[int(0.95 * (len(fs) - 1))]
         p.comm_destroy(); p.close()
-    out["clock"] = ("host wall from a common barrier until the slowest rank holds the winning solution and path "
-                    "(kgmt_plan_portfolio: peer-memory race + NCCL min-reduce + broadcast), seed = 1000*race + 1 + rank")
+    out["clock"] = ("median_ms: host wall from a common barrier until the slowest rank holds the winning solution and path "
+                    "(kgmt_plan_portfolio: peer-memory race + NCCL min-reduce + broadcast); first_solution_*: host wall from "
+                    "the latest barrier exit until the first rank's kgmt_peer_race returns solved (one CLOCK_MONOTONIC for "
+                    "all ranks of the box); seed = 1000*race + 1 + rank")
     return out
 
 
@@ -342,23 +367,23 @@ def bench_c4(k, w, local, rank, world, dist, torch, Q=1024, reps=5):
     for _ in range(reps):
         p.comm_barrier()
         t0 = time.perf_counter()
-        res, dev_ms = p.plan_batch_sharded(inits, goals, seeds, cluster_size=cs)
+        res, dev_ms = p.plan_batch_sharded(inits, goals, seeds, cluster_size=cs, as_array=True)   # kgmt_result rows, as the C ABI fills them
         wall = time.perf_counter() - t0
         tw = torch.tensor([wall], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(tw, op=dist.ReduceOp.MAX)
         wall = float(tw[0])
         if best is None or wall < best["wall_ms"] * 1e-3:
-            solved = [r for r in res if r["stop"] == 1]
-            tt = sorted(r["done_ms"] for r in solved)
-            exp = float(sum(r["expansions"] for r in res))
-            best = {"queries": Q, "gpus": world, "cluster_size": cs, "solved": len(solved),
+            ok = res["stop"] == 1
+            tt = np.sort(res["done_ms"][ok])
+            exp = float(res["expansions"].sum())
+            best = {"queries": Q, "gpus": world, "cluster_size": cs, "solved": int(ok.sum()),
                     "device_ms_max": dev_ms, "wall_ms": wall * 1e3, "queries_per_s_device": Q / dev_ms * 1e3,
                     "queries_per_s_wall": Q / wall, "expansions": exp,
                     "expansions_per_s_device": exp / dev_ms * 1e3, "expansions_per_s_wall": exp / wall,
-                    "time_to_solution_median_ms": statistics.median(tt) if tt else None,
-                    "time_to_solution_p95_ms": tt[int(0.95 * (len(tt) - 1))] if tt else None,
-                    "service_ms_median": statistics.median(r["service_ms"] for r in solved) if solved else None}
+                    "time_to_solution_median_ms": float(np.median(tt)) if len(tt) else None,
+                    "time_to_solution_p95_ms": float(tt[int(0.95 * (len(tt) - 1))]) if len(tt) else None,
+                    "service_ms_median": float(np.median(res["service_ms"][ok])) if ok.any() else None}
     p.comm_destroy(); p.close()
     return best
 
@@ -590,10 +615,10 @@ def main():
                 plan.set_seed(seed_of(args.warmup + s, j))
                 r = plan.plan(wl["init"], wl["goal"])
                 e2e_exp += r["expansions"]
-                d2h += 4 + 152                                # cull-grid item count + the planner's scalar block
+                d2h += 4 + STATE_BYTES                        # cull-grid item count + the planner's scalar block
                 if r["stop"] == 1:
                     path = plan.extract_path()
-                    d2h += 4 + 152                                # cull-grid item count + the planner's scalar block + 4 + len(path) * 28          # state block + length + the AoS-7 rows
+                    d2h += 16 + len(path) * 28                    # path header + its AoS-7 rows (one copy)
         barrier()
         e2e_s = time.perf_counter() - t1
     cfgd = plan.config()
@@ -618,13 +643,15 @@ def main():
             extra["c3"] = {"error": repr(e)}
     if "c4" not in skip:
         try:
-            extra["c4"] = bench_c4(k, w, local, rank, world, dist, torch)
-            if world > 1:
-                # the same fixed batch on ONE GPU of this box (rank 0 alone), so the line carries its own strong-scaling base
-                one = bench_c4(k, w, local, 0, 1, None, torch) if rank == 0 else None
-                torch.cuda.synchronize()
-                dist.barrier()
-                extra["c4"]["one_gpu_same_box"] = one
+            # the named batch (1 024 queries) and one that fills an 8-GPU box (8 192): strong scaling, the same Q at every N
+            for key, Q, reps in (("c4", 1024, 5), ("c4_8192", 8192, 3)):
+                extra[key] = bench_c4(k, w, local, rank, world, dist, torch, Q=Q, reps=reps)
+                if world > 1:
+                    # the same fixed batch on ONE GPU of this box (rank 0 alone), so the line carries its own strong-scaling base
+                    one = bench_c4(k, w, local, 0, 1, None, torch, Q=Q, reps=reps) if rank == 0 else None
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    extra[key]["one_gpu_same_box"] = one
         except Exception as e:
             extra["c4"] = {"error": repr(e)}
     if "c5" not in skip:

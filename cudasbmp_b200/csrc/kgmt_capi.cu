@@ -87,6 +87,8 @@ struct kgmt_ctx {
         float4 *initState = nullptr, *initCtrl = nullptr; float2* goalXY = nullptr; uint32_t* seeds = nullptr;
         DevState* states = nullptr; float* paths = nullptr;
         size_t mapIntsStride = 0;
+        /* launch configuration last resolved: the attribute / occupancy queries cost ~100 us of driver calls per batch */
+        int cfgCluster = 0, cfgCol = -1, cfgMaxClusters = 0; size_t cfgSmem = 0;
     } batch;
     unsigned epochBase = 0;
     /* sharded expansion (kgmt_shard_*) */
@@ -802,15 +804,19 @@ int kgmt_plan_batch(kgmt_ctx* ctx, const float* h_inits7, const float* h_goals7,
     CU(cudaSetDevice(ctx->device));
     kgmt_ctx::Batch& b = ctx->batch;
     batch_fn f = batch_entry(ctx->col);
-    CU(cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemBytes));
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.blockDim = dim3(TILE); cfg.dynamicSmemBytes = ctx->smemBytes; cfg.stream = ctx->stream; cfg.attrs = attr; cfg.numAttrs = 1;
     cfg.gridDim = dim3(cluster_size * 8);
-    int maxClusters = 0;
-    CU(cudaOccupancyMaxActiveClusters(&maxClusters, (const void*)f, &cfg));
+    if (b.cfgCluster != cluster_size || b.cfgCol != ctx->col || b.cfgSmem != ctx->smemBytes) {
+        CU(cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smemBytes));
+        int mc = 0;
+        CU(cudaOccupancyMaxActiveClusters(&mc, (const void*)f, &cfg));
+        b.cfgCluster = cluster_size; b.cfgCol = ctx->col; b.cfgSmem = ctx->smemBytes; b.cfgMaxClusters = mc;
+    }
+    const int maxClusters = b.cfgMaxClusters;
     if (maxClusters < 1) return fail(ctx, KGMT_ERR_CUDA, "no cluster of %d CTAs fits", cluster_size);
     const int numWs = std::min(maxClusters, Q);
     const size_t T = (size_t)ctx->p.max_tree_size, M = (size_t)ctx->maxCand;

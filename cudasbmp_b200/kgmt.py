@@ -522,8 +522,10 @@ class KGMT:
         self.treeSize_, self.costToGoal_ = r.tree_size, r.cost_to_goal
         return r.as_dict()
 
-    def plan_batch_sharded(self, inits, goals, seeds, cluster_size=0):
-        """Config 4 across the communicator: returns (results of ALL Q queries, max device ms over the ranks)."""
+    def plan_batch_sharded(self, inits, goals, seeds, cluster_size=0, as_array=False):
+        """Config 4 across the communicator: returns (results of ALL Q queries, max device ms over the ranks).
+        as_array: the results as one numpy structured array over the kgmt_result rows the library filled (no per-query
+        Python objects: building 1 024 dicts costs more than planning 1 024 queries on eight GPUs)."""
         a = _f32(inits).reshape(-1, 7)
         g = _f32(goals).reshape(-1, 7)
         sd = np.ascontiguousarray(seeds, dtype=np.uint32)
@@ -533,6 +535,8 @@ class KGMT:
         f32p = C.POINTER(C.c_float)
         self._ck(load().kgmt_plan_batch_sharded(self._h, a.ctypes.data_as(f32p), g.ctypes.data_as(f32p),
                                                 sd.ctypes.data_as(C.POINTER(C.c_uint32)), Q, int(cluster_size), res, C.byref(ms)))
+        if as_array:
+            return np.ctypeslib.as_array(res), ms.value
         return [r.as_dict() for r in res], ms.value
 
     def plan_portfolio(self, initial, goal, base_seed, race_id, max_rows=256):
