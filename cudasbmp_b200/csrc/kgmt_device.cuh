@@ -164,9 +164,11 @@ struct CollideGrid {
     __device__ __forceinline__ int cell(float v, float inv) const {
         return min(max(__float2int_rd(__fmul_rn(v, inv)), 0), C - 1);
     }
+    /* cell of a point that passed the workspace test (v > 0, or NaN which converts to 0): no lower clamp needed */
+    __device__ __forceinline__ int cell_in(float v, float inv) const { return min(__float2int_rd(__fmul_rn(v, inv)), C - 1); }
     __device__ __forceinline__ Cursor start(float x, float y) const { return Cursor{cell(x, invX), cell(y, invY), 0u}; }
     __device__ __forceinline__ bool hit(Cursor& cur, float x, float y, float bnx, float bny, float bxx, float bxy) const {
-        const int cxn = cell(x, invX), cyn = cell(y, invY);
+        const int cxn = cell_in(x, invX), cyn = cell_in(y, invY);
         const int cx0 = min(cur.cx, cxn), cx1 = max(cur.cx, cxn);
         const int cy0 = min(cur.cy, cyn), cy1 = max(cur.cy, cyn);
         cur.cx = cxn; cur.cy = cyn;
@@ -191,6 +193,55 @@ struct CollideGrid {
     }
 };
 
+/* the same walk with the CSR in SHARED memory, addressed by 32-bit shared-window addresses and explicit ld.shared:
+ * with generic pointers the compiler re-derives the shared-memory base (cluster CTA id, window, histogram offset: eleven
+ * instructions) in every trip of the row loop once registers get tight — 8 % of the kernel's warp instructions in the
+ * capture profiles/r02s_*. */
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+struct CollideGridS {
+    uint32_t startAddr, itemAddr;      /* shared-window addresses of cellStart[C*C+1] and of the float4 items */
+    int C; float invX, invY;
+    int nStart = 0, nItems = 0;
+    typedef CollideGrid::Cursor Cursor;
+    __device__ __forceinline__ int cell(float v, float inv) const {
+        return min(max(__float2int_rd(__fmul_rn(v, inv)), 0), C - 1);
+    }
+    /* cell of a point that passed the workspace test (v > 0, or NaN which converts to 0): no lower clamp needed */
+    __device__ __forceinline__ int cell_in(float v, float inv) const { return min(__float2int_rd(__fmul_rn(v, inv)), C - 1); }
+    __device__ __forceinline__ Cursor start(float x, float y) const { return Cursor{cell(x, invX), cell(y, invY), 0u}; }
+    __device__ __forceinline__ bool hit(Cursor& cur, float x, float y, float bnx, float bny, float bxx, float bxy) const {
+        const int cxn = cell_in(x, invX), cyn = cell_in(y, invY);
+        const int cx0 = min(cur.cx, cxn), cx1 = max(cur.cx, cxn);
+        const int cy0 = min(cur.cy, cyn), cy1 = max(cur.cy, cyn);
+        cur.cx = cxn; cur.cy = cyn;
+        bool h = false;
+        for (int cy = cy0; cy <= cy1 && !h; ++cy) {
+            const int row = cy * C;
+            KGMT_CHECK_RANGE(101, row + cx0, nStart); KGMT_CHECK_RANGE(102, row + cx1 + 1, nStart);
+            const int e = lds_s32(startAddr + 4u * (uint32_t)(row + cx1 + 1));
+            int k = lds_s32(startAddr + 4u * (uint32_t)(row + cx0));
+            for (; k < e && !h; k += 4) {          /* four items per trip, read unconditionally (see CollideGrid) */
+                KGMT_CHECK_RANGE(103, k, nItems); KGMT_CHECK_RANGE(104, k + 3, nItems);
+                const uint32_t a = itemAddr + 16u * (uint32_t)k;
+                const float4 o0 = lds_f4(a), o1 = lds_f4(a + 16u), o2 = lds_f4(a + 32u), o3 = lds_f4(a + 48u);
+                h = aabb_overlap(bnx, bny, bxx, bxy, o0) | aabb_overlap(bnx, bny, bxx, bxy, o1) |
+                    aabb_overlap(bnx, bny, bxx, bxy, o2) | aabb_overlap(bnx, bny, bxx, bxy, o3);
+                cur.pairs += 4u;
+            }
+        }
+        return h;
+    }
+};
+
 /* ------------------------------------------------------------------------ dynamics --
  * propagateAndCheck, src/statePropagator/statePropagator.cu:21-75, with the controls
  * already drawn.  Explicit Euler on the kinematic bicycle; per step: workspace
@@ -202,30 +253,37 @@ struct DynParams { float W, H, L; int numDisc; };
 
 struct EdgeWork { unsigned steps, pairs; };   /* loop trips of statePropagator.cu:31 executed, overlap tests executed */
 
-template <class Collide>
-__device__ __forceinline__ bool propagate_edge(float4& s, const Controls& u, const DynParams& p, const Collide& col,
-                                               EdgeWork* work = nullptr) {
-    const float dt = __fdiv_rn(u.duration, (float)p.numDisc);
-    const float tanS = tanf(u.steering);
-    const bool unitL = (p.L == 1.0f);
-    float x = s.x, y = s.y, th = s.z, v = s.w;
-    typename Collide::Cursor cur = col.start(x, y);
-    bool valid = true;
-    int i = 0;
+template <bool UNIT_L, class Collide>
+__device__ __forceinline__ bool propagate_steps(float& x, float& y, float& th, float& v, int& i, const Controls& u, const DynParams& p,
+                                                float dt, float tanS, const Collide& col, typename Collide::Cursor& cur) {
     for (; i < p.numDisc; ++i) {
         const float px = x, py = y;
         float sn, cs;
         sincosf(th, &sn, &cs);      /* one range reduction; bit-identical to sinf(th), cosf(th) (checked against the reference's kernels) */
         x = __fmaf_rn(dt, __fmul_rn(v, cs), x);
         y = __fmaf_rn(dt, __fmul_rn(v, sn), y);
-        if (x <= 0.0f || x >= p.W || y <= 0.0f || y >= p.H) { valid = false; break; }
-        const float vl = unitL ? v : __fdiv_rn(v, p.L);
+        if (x <= 0.0f || x >= p.W || y <= 0.0f || y >= p.H) return false;
+        const float vl = UNIT_L ? v : __fdiv_rn(v, p.L);
         th = __fmaf_rn(dt, __fmul_rn(vl, tanS), th);
         v = __fmaf_rn(u.a, dt, v);
         const float bnx = (px > x) ? x : px, bxx = (px > x) ? px : x;
         const float bny = (py > y) ? y : py, bxy = (py > y) ? py : y;
-        if (col.hit(cur, x, y, bnx, bny, bxx, bxy)) { valid = false; break; }
+        if (col.hit(cur, x, y, bnx, bny, bxx, bxy)) return false;
     }
+    return true;
+}
+
+template <class Collide>
+__device__ __forceinline__ bool propagate_edge(float4& s, const Controls& u, const DynParams& p, const Collide& col,
+                                               EdgeWork* work = nullptr) {
+    const float dt = __fdiv_rn(u.duration, (float)p.numDisc);
+    const float tanS = tanf(u.steering);
+    float x = s.x, y = s.y, th = s.z, v = s.w;
+    typename Collide::Cursor cur = col.start(x, y);
+    int i = 0;
+    /* v / L is exact for L = 1 (the reference's value): that loop carries no division and no test for it */
+    const bool valid = (p.L == 1.0f) ? propagate_steps<true>(x, y, th, v, i, u, p, dt, tanS, col, cur)
+                                     : propagate_steps<false>(x, y, th, v, i, u, p, dt, tanS, col, cur);
     if (work) { work->steps = (unsigned)(valid ? p.numDisc : i + 1); work->pairs = cur.pairs; }
     s = make_float4(x, y, th, v);
     return valid;

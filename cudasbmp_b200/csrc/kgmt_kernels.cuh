@@ -651,7 +651,7 @@ struct GridGroup {
  * the planner stops, on the CTAs of `grp` (all co-resident). */
 /* the collision structure as the kernels see it, staged once per launch */
 struct ColSet {
-    CollideGrid gridS, gridG;
+    CollideGridS gridS; CollideGrid gridG;
     CollideSmemAll allS, allG;
     int* hV; int* hI;                       /* per-CTA R1 histograms (shared memory) */
     TileStream stream;                      /* COL_BRUTE_STREAM only */
@@ -702,7 +702,14 @@ __device__ __forceinline__ ColSet stage_collision(const KArgs& A, unsigned char*
         __syncthreads();
         if (tid == 0) { tile_issue(ts, 0u); tile_issue(ts, 1u); }
     }
-    cs.gridS = CollideGrid{sCellStart, sItems, A.cullC, A.cullInvX, A.cullInvY, A.cellStartInts, A.numItems};
+    {
+        /* the two shared-window addresses of the staged CSR go through a warp shuffle: a value that comes out of a
+         * convergent operation cannot be re-derived inside the (divergent) row loop, so it stays in a register instead of
+         * being recomputed from the kernel parameters and special registers in every trip */
+        uint32_t sa = sCellStart ? smem_u32(sCellStart) : 0u, ia = sItems ? smem_u32(sItems) : 0u;
+        sa = __shfl_sync(0xffffffffu, sa, 0); ia = __shfl_sync(0xffffffffu, ia, 0);
+        cs.gridS = CollideGridS{sa, ia, A.cullC, A.cullInvX, A.cullInvY, A.cellStartInts, A.numItems};
+    }
     cs.gridG = CollideGrid{A.cellStart, A.cellItems, A.cullC, A.cullInvX, A.cullInvY, A.cellStartInts, A.numItems};
     cs.allS = CollideSmemAll{sObs, A.K};
     cs.allG = CollideSmemAll{A.obstacles, A.K};
@@ -728,7 +735,7 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
     DevState* st = A.st;
     int* hV = cs.hV; int* hI = cs.hI;
     const DynParams dyn{A.W, A.H, A.L, A.numDisc};
-    const CollideGrid& colGridS = cs.gridS; const CollideGrid& colGridG = cs.gridG;
+    const CollideGridS& colGridS = cs.gridS; const CollideGrid& colGridG = cs.gridG;
     const CollideSmemAll& colAllS = cs.allS; const CollideSmemAll& colAllG = cs.allG;
 
     /* every CTA keeps its own copy of the planner scalars */
@@ -795,7 +802,7 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
                     else if (canStage) staged = true;
                     else { wait_ge(&st->insertDone, S.blocksTotal); inserted = true; }
                 }
-                if (COL == COL_GRID_SMEM)        expand_chunk<CollideGrid, RECORD>(A, it, dyn, colGridS, c, lane, hV, hI, scoresOk, staged, prev);
+                if (COL == COL_GRID_SMEM)        expand_chunk<CollideGridS, RECORD>(A, it, dyn, colGridS, c, lane, hV, hI, scoresOk, staged, prev);
                 else if (COL == COL_GRID_GLOBAL) expand_chunk<CollideGrid, RECORD>(A, it, dyn, colGridG, c, lane, hV, hI, scoresOk, staged, prev);
                 else if (COL == COL_BRUTE_SMEM)  expand_chunk<CollideSmemAll, RECORD>(A, it, dyn, colAllS, c, lane, hV, hI, scoresOk, staged, prev);
                 else if (COL == COL_BRUTE_GLOBAL) expand_chunk<CollideSmemAll, RECORD>(A, it, dyn, colAllG, c, lane, hV, hI, scoresOk, staged, prev);
@@ -1110,7 +1117,7 @@ __global__ void __launch_bounds__(TILE) shard_expand_kernel(const KArgs A, int c
     const int hi = min(chunkHi, it.numChunks);
     while (c < hi) {
         if (lane == 0) t = (int)atomicAdd(&A.ticket[3], 1u);
-        if (COL == COL_GRID_SMEM)        expand_chunk<CollideGrid, false, true>(A, it, dyn, cs.gridS, c, lane, hV, hI, scoresOk);
+        if (COL == COL_GRID_SMEM)        expand_chunk<CollideGridS, false, true>(A, it, dyn, cs.gridS, c, lane, hV, hI, scoresOk);
         else if (COL == COL_GRID_GLOBAL) expand_chunk<CollideGrid, false, true>(A, it, dyn, cs.gridG, c, lane, hV, hI, scoresOk);
         else if (COL == COL_BRUTE_SMEM)  expand_chunk<CollideSmemAll, false, true>(A, it, dyn, cs.allS, c, lane, hV, hI, scoresOk);
         else                             expand_chunk<CollideSmemAll, false, true>(A, it, dyn, cs.allG, c, lane, hV, hI, scoresOk);
@@ -1602,7 +1609,7 @@ __global__ void __launch_bounds__(TILE, 3) expand_sharded_kernel(const KArgs A, 
             int c = cLo + gw, t = 0;
             while (c < cHi) {
                 if (lane == 0) t = (int)atomicAdd(ticket, 1u);
-                if (COL == COL_GRID_SMEM)        expand_chunk<CollideGrid, false, true>(As, it, dyn, cs.gridS, c, lane, hV, hI, scoresOk);
+                if (COL == COL_GRID_SMEM)        expand_chunk<CollideGridS, false, true>(As, it, dyn, cs.gridS, c, lane, hV, hI, scoresOk);
                 else if (COL == COL_GRID_GLOBAL) expand_chunk<CollideGrid, false, true>(As, it, dyn, cs.gridG, c, lane, hV, hI, scoresOk);
                 else if (COL == COL_BRUTE_SMEM)  expand_chunk<CollideSmemAll, false, true>(As, it, dyn, cs.allS, c, lane, hV, hI, scoresOk);
                 else                             expand_chunk<CollideSmemAll, false, true>(As, it, dyn, cs.allG, c, lane, hV, hI, scoresOk);
@@ -1870,12 +1877,15 @@ __global__ void __launch_bounds__(TILE) propagate_only_kernel(const KArgs A, con
         }
     }
     const DynParams dyn{A.W, A.H, A.L, A.numDisc};
+    /* shared-window addresses of the staged CSR, pinned in registers (see stage_collision) */
+    const uint32_t sStartAddr = __shfl_sync(0xffffffffu, sCellStart ? smem_u32(sCellStart) : 0u, 0);
+    const uint32_t sItemAddr = __shfl_sync(0xffffffffu, sItems ? smem_u32(sItems) : 0u, 0);
     for (long long s = (long long)blockIdx.x * TILE + tid; s < M; s += (long long)gridDim.x * TILE) {
         float4 x = __ldg(&parents[s / children]);
         const Controls u = sample_controls(slot0 + (uint32_t)s, key0, A.car);
         bool valid;
         if (COL == COL_GRID_SMEM) {
-            const CollideGrid col{sCellStart, sItems, A.cullC, A.cullInvX, A.cullInvY, A.cellStartInts, A.numItems};
+            const CollideGridS col{sStartAddr, sItemAddr, A.cullC, A.cullInvX, A.cullInvY, A.cellStartInts, A.numItems};
             valid = propagate_edge(x, u, dyn, col);
         } else if (COL == COL_GRID_GLOBAL) {
             const CollideGrid col{A.cellStart, A.cellItems, A.cullC, A.cullInvX, A.cullInvY, A.cellStartInts, A.numItems};
