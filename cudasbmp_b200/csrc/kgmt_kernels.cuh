@@ -162,6 +162,22 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+/* Pin a warp-uniform value in a register.  Values the compiler can re-derive from the kernel parameters (constant bank)
+ * or special registers are re-derived inside the hot loops whenever that saves a register — a few extra issue slots per
+ * Euler step and per cull-grid row, eleven per row for the shared-memory base of the CSR.  A value that comes back from
+ * a shuffle (addresses built from special registers) or from a volatile shared-memory load (kernel parameters: the
+ * assembler folds a shuffle of a constant) is opaque to that and has to be kept. */
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
+    uint32_t r;
+    asm volatile("shfl.sync.idx.b32 %0, %1, 0, 0x1f, 0xffffffff;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_pinned(const uint32_t* p) {
+    uint32_t r;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(r) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return r;
+}
+
 /* ------------------------------------------------------------------------- stage 1 ----
  * R1 scores, updateR1 (KGMT.cu:487-538) for any N, by one CTA of TILE threads.
  * covR uses the running count of available R2 cells (R1Cov) instead of re-summing
@@ -655,6 +671,7 @@ struct ColSet {
     CollideSmemAll allS, allG;
     int* hV; int* hI;                       /* per-CTA R1 histograms (shared memory) */
     TileStream stream;                      /* COL_BRUTE_STREAM only */
+    float W, H; int numDisc;                /* workspace size and step count, pinned in registers */
 };
 
 /* carve dynamic shared memory [R1 histograms][collision data] and stage the collision structure into it with
@@ -664,6 +681,14 @@ __device__ __forceinline__ ColSet stage_collision(const KArgs& A, unsigned char*
     const int tid = threadIdx.x;
     ColSet cs;
     cs.stream = TileStream{};
+    /* the grid resolution, the workspace size and the step count take a round trip through shared memory (pin_u32) */
+    __shared__ uint32_t sPin[8];
+    if (tid == 0) {
+        sPin[0] = (uint32_t)A.cullC; sPin[1] = __float_as_uint(A.cullInvX); sPin[2] = __float_as_uint(A.cullInvY);
+        sPin[3] = __float_as_uint(A.W); sPin[4] = __float_as_uint(A.H); sPin[5] = (uint32_t)A.numDisc;
+    }
+    __syncthreads();
+    cs.W = __uint_as_float(lds_pinned(&sPin[3])); cs.H = __uint_as_float(lds_pinned(&sPin[4])); cs.numDisc = (int)lds_pinned(&sPin[5]);
     cs.hV = reinterpret_cast<int*>(smem_raw);
     cs.hI = cs.hV + (A.useHist ? A.c1 : 0);
     unsigned char* colBase = smem_raw + (A.useHist ? ((2 * A.c1 * 4 + 15) & ~15) : 0);
@@ -707,8 +732,9 @@ __device__ __forceinline__ ColSet stage_collision(const KArgs& A, unsigned char*
          * convergent operation cannot be re-derived inside the (divergent) row loop, so it stays in a register instead of
          * being recomputed from the kernel parameters and special registers in every trip */
         uint32_t sa = sCellStart ? smem_u32(sCellStart) : 0u, ia = sItems ? smem_u32(sItems) : 0u;
-        sa = __shfl_sync(0xffffffffu, sa, 0); ia = __shfl_sync(0xffffffffu, ia, 0);
-        cs.gridS = CollideGridS{sa, ia, A.cullC, A.cullInvX, A.cullInvY, A.cellStartInts, A.numItems};
+        sa = pin_u32(sa); ia = pin_u32(ia);
+        cs.gridS = CollideGridS{sa, ia, (int)lds_pinned(&sPin[0]), __uint_as_float(lds_pinned(&sPin[1])),
+                                __uint_as_float(lds_pinned(&sPin[2])), A.cellStartInts, A.numItems};
     }
     cs.gridG = CollideGrid{A.cellStart, A.cellItems, A.cullC, A.cullInvX, A.cullInvY, A.cellStartInts, A.numItems};
     cs.allS = CollideSmemAll{sObs, A.K};
@@ -734,7 +760,8 @@ __device__ void run_plan(const KArgs& A, int maxIters, Group& grp, ColSet& cs) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     DevState* st = A.st;
     int* hV = cs.hV; int* hI = cs.hI;
-    const DynParams dyn{A.W, A.H, A.L, A.numDisc};
+    /* workspace size and step count pinned in registers (see stage_collision) */
+    const DynParams dyn{cs.W, cs.H, A.L, cs.numDisc};
     const CollideGridS& colGridS = cs.gridS; const CollideGrid& colGridG = cs.gridG;
     const CollideSmemAll& colAllS = cs.allS; const CollideSmemAll& colAllG = cs.allG;
 
@@ -1878,8 +1905,8 @@ __global__ void __launch_bounds__(TILE) propagate_only_kernel(const KArgs A, con
     }
     const DynParams dyn{A.W, A.H, A.L, A.numDisc};
     /* shared-window addresses of the staged CSR, pinned in registers (see stage_collision) */
-    const uint32_t sStartAddr = __shfl_sync(0xffffffffu, sCellStart ? smem_u32(sCellStart) : 0u, 0);
-    const uint32_t sItemAddr = __shfl_sync(0xffffffffu, sItems ? smem_u32(sItems) : 0u, 0);
+    const uint32_t sStartAddr = pin_u32(sCellStart ? smem_u32(sCellStart) : 0u);
+    const uint32_t sItemAddr = pin_u32(sItems ? smem_u32(sItems) : 0u);
     for (long long s = (long long)blockIdx.x * TILE + tid; s < M; s += (long long)gridDim.x * TILE) {
         float4 x = __ldg(&parents[s / children]);
         const Controls u = sample_controls(slot0 + (uint32_t)s, key0, A.car);
