@@ -204,7 +204,7 @@ static KArgs make_args(const kgmt_ctx* c) {
 /* choose the collision back end + shared memory, set kernel attributes, size the persistent grid */
 static int configure(kgmt_ctx* ctx) {
     const size_t histBytes = ctx->useHist ? (((size_t)2 * ctx->c1 * 4 + 15) & ~(size_t)15) : 0;
-    const size_t limit = ctx->p.reserved[0] > 0 ? (size_t)ctx->p.reserved[0] : (size_t)60 * 1024;   /* staging budget: 3 CTAs per SM */
+    const size_t limit = ctx->p.reserved[0] > 0 ? (size_t)ctx->p.reserved[0] : (size_t)66 * 1024;   /* staging budget: 3 CTAs per SM next to ~7 KB of static shared memory */
     size_t colBytes = 0;
     int col;
     if (ctx->p.collision_mode == KGMT_COLLIDE_BRUTE) {
@@ -272,6 +272,7 @@ static int configure(kgmt_ctx* ctx) {
 static int build_cull_grid(kgmt_ctx* ctx) {
     const int K = ctx->K;
     int C = ctx->p.cull_cells;
+    if (C <= 0) { const char* e = getenv("KGMT_CULL_CELLS"); if (e) C = atoi(e); }      /* experiments (scripts/ab_variants.sh) */
     if (C <= 0) C = (int)std::ceil(1.5 * std::sqrt((double)std::max(K, 1)));   /* measured on config 2: 32 -> 48 cells per side = -2.8 % plan time */
     C = std::max(1, std::min(C, 512));
     const float invX = (float)C / ctx->p.width, invY = (float)C / ctx->p.height;

@@ -207,6 +207,9 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+#ifndef KGMT_WALK_WIDTH
+#define KGMT_WALK_WIDTH 3               /* items per trip of the shared-memory cell walk */
+#endif
 struct CollideGridS {
     uint32_t startAddr, itemAddr;      /* shared-window addresses of cellStart[C*C+1] and of the float4 items */
     int C; float invX, invY;
@@ -229,13 +232,15 @@ struct CollideGridS {
             KGMT_CHECK_RANGE(101, row + cx0, nStart); KGMT_CHECK_RANGE(102, row + cx1 + 1, nStart);
             const int e = lds_s32(startAddr + 4u * (uint32_t)(row + cx1 + 1));
             int k = lds_s32(startAddr + 4u * (uint32_t)(row + cx0));
-            for (; k < e && !h; k += 4) {          /* four items per trip, read unconditionally (see CollideGrid) */
-                KGMT_CHECK_RANGE(103, k, nItems); KGMT_CHECK_RANGE(104, k + 3, nItems);
+            for (; k < e && !h; k += KGMT_WALK_WIDTH) {     /* KGMT_WALK_WIDTH items per trip, read unconditionally (see CollideGrid) */
+                KGMT_CHECK_RANGE(103, k, nItems); KGMT_CHECK_RANGE(104, k + KGMT_WALK_WIDTH - 1, nItems);
                 const uint32_t a = itemAddr + 16u * (uint32_t)k;
-                const float4 o0 = lds_f4(a), o1 = lds_f4(a + 16u), o2 = lds_f4(a + 32u), o3 = lds_f4(a + 48u);
-                h = aabb_overlap(bnx, bny, bxx, bxy, o0) | aabb_overlap(bnx, bny, bxx, bxy, o1) |
-                    aabb_overlap(bnx, bny, bxx, bxy, o2) | aabb_overlap(bnx, bny, bxx, bxy, o3);
-                cur.pairs += 4u;
+                float4 o[KGMT_WALK_WIDTH];
+#pragma unroll
+                for (int j = 0; j < KGMT_WALK_WIDTH; ++j) o[j] = lds_f4(a + 16u * (uint32_t)j);
+#pragma unroll
+                for (int j = 0; j < KGMT_WALK_WIDTH; ++j) h |= aabb_overlap(bnx, bny, bxx, bxy, o[j]);
+                cur.pairs += (unsigned)KGMT_WALK_WIDTH;
             }
         }
         return h;
