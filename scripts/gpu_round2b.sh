@@ -15,7 +15,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 1 --warmup 1 --plans-per-step 2 --only-headline > $O/${TAG}_ncu_l.log 2>&1; echo "ncu launches rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:expand_kernel -c 2 -f -o $O/${TAG}_prof \
     python bench.py --steps 1 --warmup 1 --plans-per-step 2 --only-headline > $O/${TAG}_ncu_f.log 2>&1; echo "ncu full rc=$?"
-bash scripts/gpu_sanitize.sh $TAG > $O/${TAG}_sanitize_tail.log 2>&1; echo "sanitize rc=$?"
+[ -n "$SKIP_SANITIZER" ] || bash scripts/gpu_sanitize.sh $TAG > $O/${TAG}_sanitize_tail.log 2>&1; echo "sanitize rc=$?"
 tail -5 $O/${TAG}_pytest.log
 tail -c 1500 $O/${TAG}_bench.log
-tail -30 $O/${TAG}_sanitizer.txt
+[ -n "$SKIP_SANITIZER" ] || tail -30 $O/${TAG}_sanitizer.txt
