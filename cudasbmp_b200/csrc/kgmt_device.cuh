@@ -258,43 +258,13 @@ struct DynParams { float W, H, L; int numDisc; };
 
 struct EdgeWork { unsigned steps, pairs; };   /* loop trips of statePropagator.cu:31 executed, overlap tests executed */
 
-/* sinf / cosf of one heading: the FAST path of libdevice's sincosf written out (read off the PTX nvcc emits for sincosf
- * on sm_100a: quadrant = rint(a * 2/pi), three-term Cody-Waite reduction, the two minimax polynomials, quadrant fix-up)
- * without the test for the Payne-Hanek path.  Valid for |a| < 105615 (libdevice's own bound); bit-identical to sincosf
- * there for EVERY float (tests/test_gpu_parity.py::test_sincos_fast_path_exhaustive sweeps all 2^32 patterns). */
-__device__ __forceinline__ void sincos_fast(float a, float& sn, float& cs) {
-    const int q = __float2int_rn(__fmul_rn(a, __int_as_float(0x3F22F983)));
-    const float j = __int2float_rn(q);
-    float t = __fmaf_rn(j, __int_as_float(0xBFC90FDA), a);
-    t = __fmaf_rn(j, __int_as_float(0xB3A22168), t);
-    t = __fmaf_rn(j, __int_as_float(0xA7C234C5), t);
-    const float t2 = __fmul_rn(t, t);
-    float c = __fmaf_rn(t2, __int_as_float(0x37CBAC00), __int_as_float(0xBAB607ED));
-    c = __fmaf_rn(c, t2, __int_as_float(0x3D2AAABB));
-    c = __fmaf_rn(c, t2, __int_as_float(0xBEFFFFFF));
-    c = __fmaf_rn(c, t2, 1.0f);
-    const float t3 = __fmaf_rn(t2, t, 0.0f);
-    float sv = __fmaf_rn(t2, __int_as_float(0xB94D4153), __int_as_float(0x3C0885E4));
-    sv = __fmaf_rn(sv, t2, __int_as_float(0xBE2AAAA8));
-    sv = __fmaf_rn(sv, t3, t);
-    const bool odd = (q & 1) != 0;
-    const float s1 = odd ? c : sv, c1 = odd ? sv : c;
-    sn = (q & 2) ? -s1 : s1;
-    cs = ((q + 1) & 2) ? -c1 : c1;
-}
-constexpr float SINCOS_FAST_LIMIT = 105615.0f;
-
-/* the Euler steps of one edge.  UNIT_L: v / L is exact for L = 1 (no division, no test for it in the loop).
- * FAST_TRIG: every heading of the edge is known to stay inside the fast path's range (propagate_edge bounds them before
- * the loop), so the loop carries sincos_fast and no slow-path test. */
-template <bool UNIT_L, bool FAST_TRIG, class Collide>
+template <bool UNIT_L, class Collide>
 __device__ __forceinline__ bool propagate_steps(float& x, float& y, float& th, float& v, int& i, const Controls& u, const DynParams& p,
                                                 float dt, float tanS, const Collide& col, typename Collide::Cursor& cur) {
     for (; i < p.numDisc; ++i) {
         const float px = x, py = y;
         float sn, cs;
-        if (FAST_TRIG) sincos_fast(th, sn, cs);
-        else sincosf(th, &sn, &cs); /* one range reduction; bit-identical to sinf(th), cosf(th) (checked against the reference's kernels) */
+        sincosf(th, &sn, &cs);      /* one range reduction; bit-identical to sinf(th), cosf(th) (checked against the reference's kernels) */
         x = __fmaf_rn(dt, __fmul_rn(v, cs), x);
         y = __fmaf_rn(dt, __fmul_rn(v, sn), y);
         if (x <= 0.0f || x >= p.W || y <= 0.0f || y >= p.H) return false;
@@ -316,17 +286,9 @@ __device__ __forceinline__ bool propagate_edge(float4& s, const Controls& u, con
     float x = s.x, y = s.y, th = s.z, v = s.w;
     typename Collide::Cursor cur = col.start(x, y);
     int i = 0;
-    bool valid;
-    if (p.L == 1.0f) {
-        /* |theta| after any number of steps <= |theta0| + duration * (|v0| + |a| * duration) * |tan(steer)| (each step adds
-         * dt * v_i * tan, |v_i| <= |v0| + |a| * duration); a bound well inside the fast range — NaN compares false —
-         * selects the loop without the slow-path test */
-        const float reach = __fmaf_rn(__fmul_rn(u.duration, __fmaf_rn(fabsf(u.a), u.duration, fabsf(v))), fabsf(tanS), fabsf(th));
-        if (reach < 0.5f * SINCOS_FAST_LIMIT) valid = propagate_steps<true, true>(x, y, th, v, i, u, p, dt, tanS, col, cur);
-        else                                  valid = propagate_steps<true, false>(x, y, th, v, i, u, p, dt, tanS, col, cur);
-    } else {
-        valid = propagate_steps<false, false>(x, y, th, v, i, u, p, dt, tanS, col, cur);
-    }
+    /* v / L is exact for L = 1 (the reference's value): that loop carries no division and no test for it */
+    const bool valid = (p.L == 1.0f) ? propagate_steps<true>(x, y, th, v, i, u, p, dt, tanS, col, cur)
+                                     : propagate_steps<false>(x, y, th, v, i, u, p, dt, tanS, col, cur);
     if (work) { work->steps = (unsigned)(valid ? p.numDisc : i + 1); work->pairs = cur.pairs; }
     s = make_float4(x, y, th, v);
     return valid;

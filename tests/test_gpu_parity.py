@@ -131,56 +131,6 @@ def test_bit_exact_against_reference_kernels_large_and_extreme_headings(oracle):
         assert 0.05 < valid.mean() < 0.95
 
 
-def test_sincos_fast_path_exhaustive():
-    """kgmt::sincos_fast (the fast path of libdevice's sincosf written out, used by the step loop when every heading of
-    the edge stays inside the fast range; csrc/kgmt_device.cuh) against sincosf itself for EVERY float below the fast
-    path's limit: bit for bit."""
-    import ctypes as C
-    import subprocess
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    so = os.path.join(root, "tests", "native", "libsincos_probe.so")
-    if not os.path.exists(so):
-        subprocess.check_call(["make", "-s", "-C", os.path.join(root, "tests", "native")])
-    L = C.CDLL(so)
-    out = (C.c_ulonglong * 3)()
-    assert L.sincos_probe_exhaustive(out) == 0
-    tested, bad, first = int(out[0]), int(out[1]), int(out[2])
-    assert tested > 2 * 0x47CE4700, tested          # both signs of every magnitude below 105615.0f (0x47CE4780)
-    assert bad == 0, "sincos_fast differs from sincosf for %d inputs, first pattern 0x%08x" % (bad, (first - 1) & 0xFFFFFFFF)
-
-
-def test_headings_around_the_fast_trig_bound_against_reference_kernels(oracle):
-    """Edges whose heading bound straddles the switch between the two step loops (fast-path-only trigonometry below
-    |theta| ~ 52 807, libdevice's sincosf above) and edges that cross |theta| = 105 615 where sincosf itself changes path:
-    states and flags bit for bit against the reference's propagateG."""
-    _ref_gpu_or_skip(oracle)
-    obstacles = w.c2_obstacles(1000)
-    N, n = 16, 8
-    P, children, key = 4096, 32, 4711
-    M = P * children
-    parents = w.random_parents(P, obstacles, seed=29)
-    rng = np.random.default_rng(11)
-    sign = np.where(rng.random(P) < 0.5, -1.0, 1.0)
-    centre = np.where(np.arange(P) % 2 == 0, 105615.0, 0.5 * 105615.0)
-    parents[:, 2] = (sign * (centre + rng.uniform(-8.0, 8.0, P))).astype(np.float32)
-    parents[:, 3] = rng.uniform(-30.0, 30.0, P).astype(np.float32)       # theta moves by up to ~30 * tan(steer) per edge
-    cfg = dict(w.C1, maxTreeSize=M)
-    c1, c2 = N * N, N * N * n * n
-    plan = _plan(cfg, obstacles, record_candidates=True)
-    x1, valid, u3, r1, r2 = _propagate(plan, parents, children, key, M)
-    maps = {k: np.zeros(c1 if k.startswith("R1") else c2, dtype=np.int32)
-            for k in ("R1", "R2", "R1Valid", "R2Valid", "R1Invalid", "R2Invalid", "R1Avail", "R2Avail")}
-    unx, upar, gnew, _ = oracle.ref_gpu_expand(1, children, parents, np.arange(P, dtype=np.int32), maps,
-                                               np.ones(c1, dtype=np.float32), N, n, plan.R1Size_, plan.R2Size_, 10, 1.0,
-                                               obstacles, 20.0, 20.0, key)
-    assert (bits(unx) == bits(x1)).all(), "states/controls differ from the reference kernel"
-    inside = r1 >= 0
-    assert (gnew[inside] == valid[inside]).all(), "collision flags differ from the reference kernel"
-    th1 = np.abs(unx.reshape(P, children, 7)[:, :, 2])
-    crossed = ((np.abs(parents[:, 2]) < 105615.0)[:, None] != (th1 < 105615.0))[::2].mean()
-    assert crossed > 0.02, crossed
-
-
 def test_insertion_bit_exact_against_reference_updateG(oracle):
     """scan + findInd + updateG of the reference (KGMT.cu:222-245,540-593) vs our ordered insertion."""
     _ref_gpu_or_skip(oracle)
