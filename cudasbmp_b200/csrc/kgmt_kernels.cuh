@@ -1139,7 +1139,7 @@ __global__ void __launch_bounds__(TILE) shard_expand_kernel(const KArgs A, int c
     __syncthreads();
     if (S.stop != STOP_RUNNING) return;
     const IterView it = make_view(A, S);
-    const DynParams dyn{A.W, A.H, A.L, A.numDisc};
+    const DynParams dyn{cs.W, cs.H, A.L, cs.numDisc};      /* pinned in registers by stage_collision */
     bool scoresOk = true;                  /* the scores were produced by the previous commit, stream-ordered */
     int c = chunkLo + (int)blockIdx.x * WARPS + warp;
     int t = 0;
@@ -1601,7 +1601,7 @@ __global__ void __launch_bounds__(TILE, 3) expand_sharded_kernel(const KArgs A, 
     int* hV = cs.hV; int* hI = cs.hI;
     DevState* st = A.st;
     PeerPlan* plan = P.plan;
-    const DynParams dyn{A.W, A.H, A.L, A.numDisc};
+    const DynParams dyn{cs.W, cs.H, A.L, cs.numDisc};      /* pinned in registers by stage_collision */
     const int rank = P.rank, world = P.world;
     if (tid < COPIED_WORDS) reinterpret_cast<int*>(&S)[tid] = __ldcg(reinterpret_cast<const int*>(st) + tid);
     __syncthreads();
