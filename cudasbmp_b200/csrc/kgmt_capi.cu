@@ -294,7 +294,7 @@ static int build_cull_grid(kgmt_ctx* ctx) {
     CU(cudaMemcpyAsync(ctx->hCullTotal, ctx->dCullTotal, 4, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     const int realItems = *ctx->hCullTotal;
-    const int numItems = realItems + 3;          /* + three boxes nothing overlaps: the cell walk reads four entries per trip */
+    const int numItems = realItems + 3;          /* + three boxes nothing overlaps: the cell walk reads up to four entries per trip */
     if ((size_t)numItems > ctx->cellItemsCap) {
         if (ctx->dCellItems) cudaFree(ctx->dCellItems);
         ctx->dCellItems = nullptr; ctx->cellItemsCap = 0;

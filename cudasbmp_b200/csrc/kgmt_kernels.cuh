@@ -2061,7 +2061,7 @@ __global__ void __launch_bounds__(1024) cull_scan_kernel(int* start, int cells, 
 }
 __global__ void cull_fill_kernel(const float4* obs, int K, int C, float invX, float invY, const int* start, float4* items, int total) {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell < 3)       /* the cell walk reads four entries per trip: three boxes nothing overlaps close the array */
+    if (cell < 3)       /* the cell walk reads up to four entries per trip: three boxes nothing overlaps close the array */
         items[total + cell] = make_float4(__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0xff800000), __int_as_float(0xff800000));
     if (cell >= C * C) return;
     const int cy = cell / C, cx = cell - cy * C;

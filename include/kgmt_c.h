@@ -68,7 +68,7 @@ typedef struct kgmt_params {
     int      collision_mode;         /* kgmt_collide */
     int      record_candidates;      /* 1: also keep per-candidate valid/r1/r2/u3/accept arrays for export */
     int      cull_cells;             /* cull grid is cull_cells x cull_cells; 0 = choose from the obstacle set */
-    int      reserved[5];            /* [0]: shared-memory staging budget for the collision data in bytes (0 = 60 KB);
+    int      reserved[5];            /* [0]: shared-memory staging budget for the collision data in bytes (0 = 66 KB);
                                         [1]: resident CTAs per SM of the persistent kernel (0 = all that fit);
                                         rest 0 */
     /* The car model ("systems/car.yaml" of the reference is an empty file; its dynamics and control ranges are literals
