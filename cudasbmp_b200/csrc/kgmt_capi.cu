@@ -62,6 +62,7 @@ struct kgmt_ctx {
     int cullC = 1, cellStartInts = 4, numItems = 0;
     float cullInvX = 0.f, cullInvY = 0.f;
     float* hObsPinned = nullptr; size_t hObsPinnedCap = 0;            /* pinned staging of kgmt_set_obstacles_host */
+    int cullExpect = -1;                                              /* >= 0: item count computed on the host, to be checked against *hCullTotal */
     int* hCullTotal = nullptr; int* dCullTotal = nullptr;             /* item count of the cull grid: pinned host word, device word */
     std::vector<unsigned char> hPath;  /* staging of kgmt_extract_path */
     /* staging */
@@ -269,7 +270,15 @@ static int configure(kgmt_ctx* ctx) {
 
 /* uniform grid over the workspace: CSR of obstacle AABBs per cell, built ON THE DEVICE from ctx->dObs (cull_* kernels);
  * the host learns one number, the item count, which sizes the shared-memory staging of the planner kernels */
-static int build_cull_grid(kgmt_ctx* ctx) {
+/* cell of one coordinate as cull_cell_of computes it on the device (round-down conversion saturates, NaN -> 0) */
+static inline int host_cull_cell(float v, float inv, int C) {
+    const float t = v * inv;
+    if (!(t > 0.0f)) return 0;
+    if (t >= (float)C) return C - 1;
+    return std::min((int)floorf(t), C - 1);
+}
+
+static int build_cull_grid(kgmt_ctx* ctx, const float* h_aabb = nullptr) {
     const int K = ctx->K;
     int C = ctx->p.cull_cells;
     if (C <= 0) { const char* e = getenv("KGMT_CULL_CELLS"); if (e) C = atoi(e); }      /* experiments (scripts/ab_variants.sh) */
@@ -288,12 +297,30 @@ static int build_cull_grid(kgmt_ctx* ctx) {
     if (!ctx->hCullTotal) CU(cudaHostAlloc(&ctx->hCullTotal, 16, cudaHostAllocDefault));
     if (!ctx->dCullTotal) CU(cudaMalloc(&ctx->dCullTotal, 16));
     CU(cudaMemsetAsync(ctx->dCellStart, 0, (size_t)startInts * 4, s));
-    cull_count_kernel<<<(cells + 127) / 128, 128, 0, s>>>(ctx->dObs, K, C, invX, invY, ctx->dCellStart);
+    cull_count_kernel<<<(cells * 32 + 255) / 256, 256, 0, s>>>(ctx->dObs, K, C, invX, invY, ctx->dCellStart);      /* a warp per cell */
     cull_scan_kernel<<<1, 1024, 0, s>>>(ctx->dCellStart, cells, startInts, ctx->dCullTotal);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(ctx->hCullTotal, ctx->dCullTotal, 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    const int realItems = *ctx->hCullTotal;
+    int realItems;
+    if (h_aabb) {
+        /* the caller's obstacles are on the host: the item count (all that sizes the shared-memory staging) is a sum over
+         * the obstacles of the cells they span — no need to wait for the device's scan; the device's own total is checked
+         * against it at the next synchronisation (fetch_state) */
+        long long sum = 0;
+        for (int k = 0; k < K; ++k) {
+            const float* o = h_aabb + (size_t)k * 4;
+            const long long nx = (long long)host_cull_cell(o[2], invX, C) - host_cull_cell(o[0], invX, C) + 1;
+            const long long ny = (long long)host_cull_cell(o[3], invY, C) - host_cull_cell(o[1], invY, C) + 1;
+            if (nx > 0 && ny > 0) sum += nx * ny;
+        }
+        if (sum > 0x7fffff00LL) return fail(ctx, KGMT_ERR_INVALID, "cull grid too large (%lld items)", sum);
+        realItems = (int)sum;
+        ctx->cullExpect = realItems;
+    } else {
+        CU(cudaStreamSynchronize(s));
+        realItems = *ctx->hCullTotal;
+        ctx->cullExpect = -1;
+    }
     const int numItems = realItems + 3;          /* + three boxes nothing overlaps: the cell walk reads up to four entries per trip */
     if ((size_t)numItems > ctx->cellItemsCap) {
         if (ctx->dCellItems) cudaFree(ctx->dCellItems);
@@ -302,7 +329,7 @@ static int build_cull_grid(kgmt_ctx* ctx) {
         CU(cudaMalloc(&ctx->dCellItems, cap * 16));
         ctx->cellItemsCap = cap;
     }
-    cull_fill_kernel<<<(cells + 127) / 128, 128, 0, s>>>(ctx->dObs, K, C, invX, invY, ctx->dCellStart, ctx->dCellItems, realItems);
+    cull_fill_kernel<<<(cells * 32 + 255) / 256, 256, 0, s>>>(ctx->dObs, K, C, invX, invY, ctx->dCellStart, ctx->dCellItems, realItems);
     CU(cudaGetLastError());
     ctx->launches += 3;
     ctx->cullC = C; ctx->cullInvX = invX; ctx->cullInvY = invY; ctx->cellStartInts = startInts; ctx->numItems = numItems;
@@ -310,13 +337,13 @@ static int build_cull_grid(kgmt_ctx* ctx) {
 }
 
 /* obstacles are on the device in ctx->dObs[0, K) (copied there by the caller): pad to whole stream tiles, build the grid */
-static int install_obstacles(kgmt_ctx* ctx) {
+static int install_obstacles(kgmt_ctx* ctx, const float* h_aabb = nullptr) {
     const int K = ctx->K;
     const int padded = (int)ctx->obsCap;
     if (padded > K) cull_pad_kernel<<<(padded - K + 255) / 256, 256, 0, ctx->stream>>>(ctx->dObs, K, padded);
     CU(cudaGetLastError());
     ctx->launches += 1;
-    int rc = build_cull_grid(ctx);
+    int rc = build_cull_grid(ctx, h_aabb);
     if (rc) return rc;
     return configure(ctx);
 }
@@ -409,6 +436,12 @@ static int reset_loop_bookkeeping(kgmt_ctx* ctx) {
 static int fetch_state(kgmt_ctx* ctx) {
     CU(cudaMemcpyAsync(ctx->hState, ctx->dState, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->cullExpect >= 0) {                /* the device's scan of the cull grid against the host's count (build_cull_grid) */
+        const int expect = ctx->cullExpect;
+        ctx->cullExpect = -1;
+        if (*ctx->hCullTotal != expect)
+            return fail(ctx, KGMT_ERR_STATE, "cull grid: device counted %d items, host %d", *ctx->hCullTotal, expect);
+    }
     if (ctx->hState->iterationsDone > 0) ctx->dirtyCand = ctx->maxCand;
     return KGMT_OK;
 }
@@ -673,7 +706,7 @@ int kgmt_set_obstacles_host(kgmt_ctx* ctx, const float* h_aabb, int K) {
         CU(cudaMemcpyAsync(ctx->dObs, ctx->hObsPinned, (size_t)K * 16, cudaMemcpyHostToDevice, ctx->stream));
     }
     ctx->K = K;
-    return install_obstacles(ctx);
+    return install_obstacles(ctx, K > 0 ? h_aabb : nullptr);
 }
 
 int kgmt_set_obstacles(kgmt_ctx* ctx, const float* d_aabb, int K) {

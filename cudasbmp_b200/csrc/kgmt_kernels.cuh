@@ -2020,17 +2020,20 @@ __global__ void cull_pad_kernel(float4* obs, int K, int padded) {
     const int k = K + blockIdx.x * blockDim.x + threadIdx.x;     /* boxes nothing can overlap (min = +inf, max = -inf) */
     if (k < padded) obs[k] = make_float4(__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0xff800000), __int_as_float(0xff800000));
 }
+/* one WARP per cell: lanes stride the obstacle array, the counts are summed by shuffles */
 __global__ void cull_count_kernel(const float4* obs, int K, int C, float invX, float invY, int* start /* [C*C+1], zeroed */) {
-    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= C * C) return;
+    const int cell = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (cell >= C * C) return;                                   /* whole warps leave together */
     const int cy = cell / C, cx = cell - cy * C;
     int n = 0;
-    for (int k = 0; k < K; ++k) {
+    for (int k = lane; k < K; k += 32) {
         const float4 o = __ldg(&obs[k]);
         n += (cull_cell_of(o.x, invX, C) <= cx) & (cx <= cull_cell_of(o.z, invX, C)) &
              (cull_cell_of(o.y, invY, C) <= cy) & (cy <= cull_cell_of(o.w, invY, C));
     }
-    start[cell + 1] = n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (lane == 0) start[cell + 1] = n;
 }
 /* one CTA: start[i] = sum of the counts before cell i (in place), the padding words = the total; *total too */
 __global__ void __launch_bounds__(1024) cull_scan_kernel(int* start, int cells, int startInts, int* total) {
@@ -2059,18 +2062,28 @@ __global__ void __launch_bounds__(1024) cull_scan_kernel(int* start, int cells, 
     for (int i = cells + 1 + tid; i < startInts; i += 1024) start[i] = t;
     if (tid == 0) *total = t;
 }
+/* one WARP per cell, 32 obstacles per trip: the ballot of the lanes whose obstacle touches the cell gives every such
+ * obstacle its place, in obstacle order — the same CSR the one-thread-per-cell fill produced, in 1/32 of the trips */
 __global__ void cull_fill_kernel(const float4* obs, int K, int C, float invX, float invY, const int* start, float4* items, int total) {
-    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell < 3)       /* the cell walk reads up to four entries per trip: three boxes nothing overlaps close the array */
-        items[total + cell] = make_float4(__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0xff800000), __int_as_float(0xff800000));
+    const int gid = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    const int cell = gid >> 5, lane = threadIdx.x & 31;
+    if (gid < 3)        /* the cell walk reads up to four entries per trip: three boxes nothing overlaps close the array */
+        items[total + gid] = make_float4(__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0xff800000), __int_as_float(0xff800000));
     if (cell >= C * C) return;
     const int cy = cell / C, cx = cell - cy * C;
     int at = start[cell];
-    for (int k = 0; k < K; ++k) {
-        const float4 o = __ldg(&obs[k]);
-        if ((cull_cell_of(o.x, invX, C) <= cx) & (cx <= cull_cell_of(o.z, invX, C)) &
-            (cull_cell_of(o.y, invY, C) <= cy) & (cy <= cull_cell_of(o.w, invY, C)))
-            items[at++] = o;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const int k = k0 + lane;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool in = false;
+        if (k < K) {
+            o = __ldg(&obs[k]);
+            in = (cull_cell_of(o.x, invX, C) <= cx) & (cx <= cull_cell_of(o.z, invX, C)) &
+                 (cull_cell_of(o.y, invY, C) <= cy) & (cy <= cull_cell_of(o.w, invY, C));
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (in) items[at + __popc(bal & ((1u << lane) - 1u))] = o;
+        at += __popc(bal);
     }
 }
 
