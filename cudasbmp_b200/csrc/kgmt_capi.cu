@@ -32,6 +32,7 @@ struct kgmt_ctx {
     cudaStream_t stream = nullptr;      /* the stream every call launches on */
     cudaStream_t ownStream = nullptr;   /* created by kgmt_create; `stream` unless the caller installed its own */
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evState = nullptr, evPath = nullptr;      /* kgmt_plan: scalars landed / prefetched path landed (no timing) */
     /* device memory */
     float4 *treeState = nullptr, *treeCtrl = nullptr;
     int* treeParent = nullptr;
@@ -65,6 +66,10 @@ struct kgmt_ctx {
     int cullExpect = -1;                                              /* >= 0: item count computed on the host, to be checked against *hCullTotal */
     int* hCullTotal = nullptr; int* dCullTotal = nullptr;             /* item count of the cull grid: pinned host word, device word */
     std::vector<unsigned char> hPath;  /* staging of kgmt_extract_path */
+    /* solution path of the last kgmt_plan, traced behind the planner kernel and copied with the scalars: valid while no
+     * kernel of this library has run since (launch counter) and the scalars still name the same goal node */
+    unsigned char* dPathPre = nullptr; unsigned char* hPathPre = nullptr;
+    long long pathPreLaunches = -1; int pathPreGoal = -1, pathPreTree = 0;
     /* staging */
     void* scratch = nullptr; size_t scratchBytes = 0;
     float4* dParents = nullptr; size_t parentsCap = 0;
@@ -171,6 +176,9 @@ static fused_fn fused_entry(int col) {
         default: return expand_sharded_kernel<COL_BRUTE_GLOBAL>;
     }
 }
+
+constexpr int PATH_PRE_ROWS = 128;                               /* rows of the path prefetched by kgmt_plan */
+constexpr size_t PATH_PRE_BYTES = 16 + (size_t)PATH_PRE_ROWS * 28;
 
 static KArgs make_args(const kgmt_ctx* c) {
     KArgs A{};
@@ -408,6 +416,7 @@ static int clear_state(kgmt_ctx* ctx, bool sync, bool light = false) {
     ctx->dirtyCand = 0;
     ctx->begun = false;
     ctx->haveCkpt = false;
+    ctx->pathPreLaunches = -1;
     if (light) return KGMT_OK;
     fill_float_kernel<<<(2 * ctx->c1 + 255) / 256, 256, 0, ctx->stream>>>(ctx->R1Score[0], 1.0f, (size_t)2 * ctx->c1);
     DevState z{};
@@ -433,9 +442,8 @@ static int reset_loop_bookkeeping(kgmt_ctx* ctx) {
     return KGMT_OK;
 }
 
-static int fetch_state(kgmt_ctx* ctx) {
-    CU(cudaMemcpyAsync(ctx->hState, ctx->dState, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+/* after the scalars have landed in *hState */
+static int fetch_state_landed(kgmt_ctx* ctx) {
     if (ctx->cullExpect >= 0) {                /* the device's scan of the cull grid against the host's count (build_cull_grid) */
         const int expect = ctx->cullExpect;
         ctx->cullExpect = -1;
@@ -444,6 +452,12 @@ static int fetch_state(kgmt_ctx* ctx) {
     }
     if (ctx->hState->iterationsDone > 0) ctx->dirtyCand = ctx->maxCand;
     return KGMT_OK;
+}
+
+static int fetch_state(kgmt_ctx* ctx) {
+    CU(cudaMemcpyAsync(ctx->hState, ctx->dState, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return fetch_state_landed(ctx);
 }
 
 static void fill_result(const kgmt_ctx* ctx, kgmt_result* out, float ms) {
@@ -575,10 +589,12 @@ void kgmt_destroy(kgmt_ctx* ctx) {
     cudaFree(ctx->dObs); cudaFree(ctx->dCellStart); cudaFree(ctx->dCellItems); cudaFree(ctx->dCullTotal);
     if (ctx->hObsPinned) cudaFreeHost(ctx->hObsPinned);
     if (ctx->hCullTotal) cudaFreeHost(ctx->hCullTotal);
-    cudaFree(ctx->scratch); cudaFree(ctx->dParents);
+    cudaFree(ctx->scratch); cudaFree(ctx->dParents); cudaFree(ctx->dPathPre); if (ctx->hPathPre) cudaFreeHost(ctx->hPathPre);
     free_batch(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->evState) cudaEventDestroy(ctx->evState);
+    if (ctx->evPath) cudaEventDestroy(ctx->evPath);
     if (ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
     cudaFree(ctx->peer.block); cudaFree(ctx->peer.plan); cudaFree(ctx->peer.dRaceFlags);
     if (ctx->peer.hPlan) cudaFreeHost(ctx->peer.hPlan);
@@ -627,6 +643,8 @@ int kgmt_create(const kgmt_params* p, kgmt_ctx** out) {
     ctx->stream = ctx->ownStream;
     CU(cudaEventCreate(&ctx->ev0));
     CU(cudaEventCreate(&ctx->ev1));
+    CU(cudaEventCreateWithFlags(&ctx->evState, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->evPath, cudaEventDisableTiming));
 
     const int N = p->N, n = p->n;
     ctx->c1 = N * N;
@@ -794,8 +812,26 @@ int kgmt_plan(kgmt_ctx* ctx, const float* initial7, const float* goal7, kgmt_res
     { int rc = launch_expand(ctx, 0x7fffffff); if (rc) return rc; }
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->begun = true;
-    int rc = fetch_state(ctx);
+    /* the solution's back-trace rides along: one more small kernel behind the planner (outside the event pair), its rows
+     * in the same synchronisation as the scalars — kgmt_extract_path of the goal node is then a host copy */
+    if (!ctx->dPathPre) {
+        CU(cudaMalloc(&ctx->dPathPre, PATH_PRE_BYTES));
+        CU(cudaHostAlloc(&ctx->hPathPre, PATH_PRE_BYTES, cudaHostAllocDefault));
+    }
+    /* order on the stream: scalars -> [evState] -> back-trace kernel -> path rows -> [evPath].  kgmt_plan returns as soon as
+     * the scalars have landed; the back-trace finishes behind the caller's back and kgmt_extract_path waits on evPath */
+    CU(cudaMemcpyAsync(ctx->hState, ctx->dState, sizeof(DevState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->evState, ctx->stream));
+    trace_goal_kernel<<<1, 32, 0, ctx->stream>>>(A, (int*)ctx->dPathPre, (float*)(ctx->dPathPre + 16), PATH_PRE_ROWS);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    CU(cudaMemcpyAsync(ctx->hPathPre, ctx->dPathPre, PATH_PRE_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(ctx->evPath, ctx->stream));
+    ctx->pathPreLaunches = -1;
+    CU(cudaEventSynchronize(ctx->evState));
+    int rc = fetch_state_landed(ctx);
     if (rc) return rc;
+    ctx->pathPreLaunches = ctx->launches; ctx->pathPreGoal = ctx->hState->goalIdx; ctx->pathPreTree = ctx->hState->treeSize;
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (out) fill_result(ctx, out, ms);
@@ -1514,6 +1550,7 @@ int kgmt_restore(kgmt_ctx* ctx) {
     if (!ctx) return KGMT_ERR_INVALID;
     if (!ctx->haveCkpt) return fail(ctx, KGMT_ERR_STATE, "kgmt_restore without kgmt_checkpoint");
     CU(cudaSetDevice(ctx->device));
+    ctx->pathPreLaunches = -1;
     int rc = fetch_state(ctx);
     if (rc) return rc;
     CU(cudaMemcpyAsync(ctx->mapSlab, ctx->mapSlabCkpt, ctx->mapSlabInts * 4, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1667,6 +1704,18 @@ int kgmt_extract_path(kgmt_ctx* ctx, int node, float* h_rows7, int max_rows) {
     const int T = ctx->hState->treeSize;
     if (node < 0) node = ctx->hState->goalIdx;
     if (node < 0 || node >= T) return fail(ctx, KGMT_ERR_INVALID, "no such node %d (tree size %d)", node, T);
+    if (!ctx->peer.inFlight && ctx->hPathPre && ctx->pathPreLaunches == ctx->launches && node == ctx->pathPreGoal &&
+        T == ctx->pathPreTree) {
+        /* traced by kgmt_plan behind the planner kernel and nothing has run since */
+        CU(cudaEventSynchronize(ctx->evPath));
+        int len = 0;
+        memcpy(&len, ctx->hPathPre, 4);
+        if (len >= 0 && len <= PATH_PRE_ROWS) {
+            const size_t rows = std::min<size_t>((size_t)len, (size_t)std::max(max_rows, 0));
+            if (rows) memcpy(h_rows7, ctx->hPathPre + 16, rows * 28);
+            return len;
+        }
+    }
     /* back-trace on the device (the parent links are L2-resident), then ONE device-to-host copy of the length and the
      * first rows (solution paths are a few dozen nodes); a second copy only for longer chains */
     const size_t rowsCap = (size_t)std::max(max_rows, 0);

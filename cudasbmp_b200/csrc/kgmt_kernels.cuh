@@ -2203,6 +2203,32 @@ __global__ void trace_path_kernel(const KArgs A, int node, int treeSize, int* ou
     }
 }
 
+/* the same for the goal node of the plan that has just run, node and tree size read from the planner's scalars on the
+ * device (kgmt_plan launches it behind the planner kernel, so the path travels with the scalars in one copy) */
+__global__ void trace_goal_kernel(const KArgs A, int* outLen, float* rows7, int maxRows) {
+    const int lane = threadIdx.x;
+    const DevState* st = A.st;
+    const int node = (*(volatile const int*)&st->stop == STOP_SOLVED) ? *(volatile const int*)&st->goalIdx : -1;
+    const int treeSize = *(volatile const int*)&st->treeSize;
+    if (node < 0 || node >= treeSize) { if (lane == 0) *outLen = -1; return; }
+    int len = 0;
+    if (lane == 0) {
+        for (int v = node; v >= 0 && len <= treeSize; v = __ldcg(&A.treeParent[v])) ++len;
+        *outLen = len;
+    }
+    len = __shfl_sync(0xffffffffu, len, 0);
+    int v = node, at = len - 1;
+    for (int i = 0; i < lane && v >= 0; ++i) { v = __ldcg(&A.treeParent[v]); --at; }
+    while (v >= 0 && at >= 0) {
+        if (at < maxRows) {
+            const float4 x = __ldcg(&A.treeState[v]), u = __ldcg(&A.treeCtrl[v]);
+            float* o = rows7 + (size_t)at * 7;
+            o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w; o[4] = u.x; o[5] = u.y; o[6] = u.z;
+        }
+        for (int i = 0; i < 32 && v >= 0; ++i) { v = __ldcg(&A.treeParent[v]); --at; }
+    }
+}
+
 /* views in the reference's element layout (export) */
 __global__ void gather_samples_kernel(const float4* st, const float4* ct, float* out7, int count, int costIsU3) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
