@@ -160,10 +160,13 @@ int  kgmt_reset(kgmt_ctx* ctx);                                 /* re-plan witho
 
 /* ---- obstacles: float[K][4] = (minx, miny, maxx, maxy), obstacles.csv:1-5 ------------------ */
 int  kgmt_set_obstacles(kgmt_ctx* ctx, const float* d_aabb, int K);      /* DEVICE pointer, as plan()'s d_obstacles (KGMT.cuh:31, main.cu:60-62); copied */
-int  kgmt_set_obstacles_host(kgmt_ctx* ctx, const float* h_aabb, int K); /* HOST pointer (what readObstaclesFromCSV returns, helper.cu:11-34) */
+int  kgmt_set_obstacles_host(kgmt_ctx* ctx, const float* h_aabb, int K); /* HOST pointer (what readObstaclesFromCSV returns, helper.cu:11-34);
+                                                                            asynchronous: staged in pinned memory, the cull grid is built on the
+                                                                            device behind the upload, nothing waits before the next plan */
 
 /* ---- planning ------------------------------------------------------------------------------ */
-/* KGMT::plan (KGMT.cuh:31, KGMT.cu:80-317) without the CSV dump: initial/goal are HOST float[7]. */
+/* KGMT::plan (KGMT.cuh:31, KGMT.cu:80-317) without the CSV dump: initial/goal are HOST float[7].  Returns when the planner's
+ * scalars are on the host; the back-trace of the goal path runs behind it on the same stream (kgmt_extract_path below). */
 int  kgmt_plan(kgmt_ctx* ctx, const float* initial7, const float* goal7, kgmt_result* out);
 /* the same, split: root insertion (KGMT.cu:85-114) then one while-loop body (KGMT.cu:118-259) per call */
 int  kgmt_begin(kgmt_ctx* ctx, const float* initial7, const float* goal7);
@@ -171,8 +174,10 @@ int  kgmt_expand_iteration(kgmt_ctx* ctx, kgmt_iter_stats* out);
 /* up to `count` loop bodies in one launch (stops early when the planner stops); `out` = the last one executed */
 int  kgmt_expand_iterations(kgmt_ctx* ctx, int count, kgmt_iter_stats* out);
 int  kgmt_get_result(kgmt_ctx* ctx, kgmt_result* out);
-/* back-trace of the parent links from the goal node (or any node) to the root: rows of 7 floats,
- * root first.  Returns the path length (may exceed max_rows; only max_rows are written). */
+/* back-trace of the parent links from the goal node (node < 0) or any node to the root: rows of 7 floats,
+ * root first.  Returns the path length (may exceed max_rows; only max_rows are written).  For the goal node of the
+ * kgmt_plan that has just returned (paths up to 128 nodes) the rows are already on their way: an event wait and a host
+ * copy, no kernel. */
 int  kgmt_extract_path(kgmt_ctx* ctx, int node, float* h_rows7, int max_rows);
 
 /* ---- batched planning (BASELINE config 4) ----------------------------------------------------------------------
